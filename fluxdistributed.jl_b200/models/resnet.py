@@ -1,0 +1,117 @@
+"""Model zoo (reference E1: Metalhead ``ResNet34()`` / ``ResNet()``; tiny test net
+``test/single_device.jl:119``).
+
+ResNet-18/34 use BasicBlock, ResNet-50/101/152 Bottleneck (v1.5: stride on the 3x3).
+Parameter counts match SURVEY App. A: ResNet-34 21,797,672; ResNet-50 25,557,032.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from ..nn.layers import ConvBN, Head, MaxPool
+
+
+class BasicBlock(nn.Module):
+    expansion = 1
+
+    def __init__(self, cin: int, planes: int, stride: int = 1):
+        super().__init__()
+        self.conv1 = ConvBN(cin, planes, 3, stride, relu=True)
+        self.conv2 = ConvBN(planes, planes, 3, 1, relu=True)  # relu applied after the residual add
+        self.downsample = None
+        if stride != 1 or cin != planes:
+            self.downsample = ConvBN(cin, planes, 1, stride, padding=0, relu=False)
+
+    def forward(self, x):
+        idn = x if self.downsample is None else self.downsample(x)
+        return self.conv2(self.conv1(x), residual=idn)
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, cin: int, planes: int, stride: int = 1):
+        super().__init__()
+        cout = planes * 4
+        self.conv1 = ConvBN(cin, planes, 1, 1, padding=0, relu=True)
+        self.conv2 = ConvBN(planes, planes, 3, stride, relu=True)
+        self.conv3 = ConvBN(planes, cout, 1, 1, padding=0, relu=True)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = ConvBN(cin, cout, 1, stride, padding=0, relu=False)
+
+    def forward(self, x):
+        idn = x if self.downsample is None else self.downsample(x)
+        return self.conv3(self.conv2(self.conv1(x)), residual=idn)
+
+
+class ResNet(nn.Module):
+    def __init__(self, block, layers: Sequence[int], nclasses: int = 1000, in_ch: int = 3):
+        super().__init__()
+        self.stem = ConvBN(in_ch, 64, 7, 2, padding=3, relu=True)
+        self.pool = MaxPool(3, 2, 1)
+        cin = 64
+        stages: List[nn.Module] = []
+        for i, (planes, n) in enumerate(zip((64, 128, 256, 512), layers)):
+            blocks = []
+            for j in range(n):
+                blocks.append(block(cin, planes, stride=(2 if (i > 0 and j == 0) else 1)))
+                cin = planes * block.expansion
+            stages.append(nn.Sequential(*blocks))
+        self.layer1, self.layer2, self.layer3, self.layer4 = stages
+        self.head = Head(cin, nclasses)
+        self.nclasses = nclasses
+
+    def features(self, x):
+        x = self.pool(self.stem(x))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+    def forward(self, x):
+        return self.head(self.features(x))
+
+
+def ResNet18(nclasses: int = 1000) -> ResNet:
+    return ResNet(BasicBlock, (2, 2, 2, 2), nclasses)
+
+
+def ResNet34(nclasses: int = 1000) -> ResNet:
+    return ResNet(BasicBlock, (3, 4, 6, 3), nclasses)
+
+
+def ResNet50(nclasses: int = 1000) -> ResNet:
+    return ResNet(Bottleneck, (3, 4, 6, 3), nclasses)
+
+
+def ResNet101(nclasses: int = 1000) -> ResNet:
+    return ResNet(Bottleneck, (3, 4, 23, 3), nclasses)
+
+
+def ResNet152(nclasses: int = 1000) -> ResNet:
+    return ResNet(Bottleneck, (3, 8, 36, 3), nclasses)
+
+
+def resnet_trunk_with_head(nfeat_classes: int = 1000, nout: int = 200) -> nn.Module:
+    """The process-mode default model: ``Chain(ResNet().layers[1:end-1], Dense(1000, 200))``
+    (``src/sync.jl:215``) — a ResNet-50 whose 1000-way output feeds a 200-way Dense."""
+    return nn.Sequential(ResNet50(nfeat_classes), nn.Linear(nfeat_classes, nout))
+
+
+class TinyConvNet(nn.Module):
+    """``Chain(Conv((7,7),3=>3), flatten, Dense(2028,10))`` on 32x32x3
+    (``test/single_device.jl:119``): 26*26*3 = 2028 features."""
+
+    def __init__(self, nclasses: int = 10, in_hw: int = 32):
+        super().__init__()
+        self.conv = nn.Conv2d(3, 3, 7)
+        self.flatten = nn.Flatten()
+        self.dense = nn.Linear(3 * (in_hw - 6) ** 2, nclasses)
+
+    def forward(self, x):
+        return self.dense(self.flatten(self.conv(x)))
+
+
+def tiny_convnet(nclasses: int = 10) -> TinyConvNet:
+    return TinyConvNet(nclasses)

@@ -1,0 +1,59 @@
+"""Op layer: Python entry points of the hand-written sm_100a kernels in ``csrc/``
+plus their PyTorch reference implementations (the numerics oracle and the
+CPU fallback).  SURVEY §2.5 maps each kernel to the reference call site it
+replaces.
+
+The extension is built in-tree (``_C*.so`` next to this package, see
+``build.py``); on a CUDA box the native path *must* be present — callers that ask
+for it get a loud error instead of a silent PyTorch fallback.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+from typing import Optional
+
+import torch
+
+_C = None
+_C_ERR: Optional[BaseException] = None
+
+
+def _load():
+    global _C, _C_ERR
+    if _C is not None or _C_ERR is not None:
+        return _C
+    try:
+        _C = importlib.import_module("fluxdist._C")
+    except BaseException as e:  # noqa: BLE001 - recorded and re-raised by require_native
+        _C_ERR = e
+        _C = None
+    return _C
+
+
+def native_available() -> bool:
+    """True when the sm_100a extension is importable *and* a CUDA device exists."""
+    if os.environ.get("FLUXDIST_DISABLE_NATIVE") == "1":
+        return False
+    return torch.cuda.is_available() and _load() is not None
+
+
+def extension():
+    """The loaded extension module (imports on CPU too, for build checks)."""
+    m = _load()
+    if m is None:
+        raise RuntimeError(f"fluxdist native extension not built/loadable: {_C_ERR!r}; run "
+                           f"`python -c 'import __graft_entry__ as g; g.build()'`")
+    return m
+
+
+def require_native() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("native sm_100a path requested but no CUDA device is visible")
+    extension()
+
+
+from .reference import (bn_apply_ref, bn_bwd_ref, bn_stats_ref, conv_bn_act_ref, conv_dgrad_ref,  # noqa: E402
+                        conv_fprop_ref, conv_wgrad_ref, softmax_ce_ref)
+from .native import (bn_apply, bn_bwd, bn_stats, conv_bn_act, conv_dgrad, conv_fprop, conv_wgrad,  # noqa: E402
+                     fused_update_local, gap_linear, gemm_nt, maxpool2d, normalize_u8, softmax_ce)

@@ -1,0 +1,328 @@
+"""The fused gradient-exchange + optimiser engine (the B200 product path).
+
+What the reference does per step (``src/ddp_tasks.jl:59-109,163-172``) in
+~(N+2)·L small launches plus 2·L·N peer copies — gather grads to HOST, N-1 add
+passes, a divide pass, broadcast back, per-tensor optimiser — is here ONE kernel
+launch per replica over flat arenas:
+
+    barrier-in -> reduce my slice from every peer (P2P ``ld.global`` or in-switch
+    ``multimem.ld_reduce``) -> x 1/N -> Momentum/Adam in registers on the fp32
+    master shard -> store new weights (bf16 and/or fp32) to every replica
+    (P2P stores or ``multimem.st``) -> barrier-out
+
+* ``FlatArena``     one allocation each for master weights, gradients, moments
+                    and (optionally) bf16 compute weights; identical layout on
+                    every replica so a single offset addresses all peers.
+* ``FusedReplica``  a model bound to its arena: ``p.data``/``p.grad`` are views,
+                    so autograd (or the native wgrad kernels) write gradients
+                    straight into the arena — the reference's ``markbuffer!``
+                    copies disappear.
+* ``FusedGroup``    N replicas plus a communicator:
+    ``NativeComm``  hand-written sm_100a kernel over peer-mapped memory
+                    (threads of one process via UVA peer access, or processes
+                    via torch symmetric memory + NVLS multicast),
+    ``ThreadComm``  CPU / no-extension oracle for task mode,
+    ``DistComm``    ``torch.distributed`` all-reduce (gloo on CPU; on CUDA this
+                    is the "only calls NCCL" *baseline*, never the default).
+
+Two-shot shards the update work and the moments by owner rank (ZeRO-1-like);
+``state_trees()`` re-assembles the logical per-replica optimiser state the
+reference API exposes (``sts[dev]``).
+"""
+from __future__ import annotations
+
+import math
+import threading
+from typing import Any, Callable, Dict, List, Optional, Sequence
+
+import torch
+from torch import nn
+
+from ..devices import as_device, device_ctx
+from ..optim import Rule, flat_step
+from ..optim.rules import RULE_ADAM, RULE_ADAMW
+from ..tree import Tree, _module_tree
+
+ALIGN = 2048  # elements; keeps every rank slice 16B-aligned for v4 accesses at any N<=8 and bf16
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class FlatArena:
+    """Flat, identically laid out buffers for one replica."""
+
+    def __init__(self, model: nn.Module, device: torch.device, n_slots: int, lowp: Optional[torch.dtype],
+                 world: int, alloc: Optional[Callable[[int, torch.dtype], torch.Tensor]] = None):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        self.offsets: List[int] = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += _round_up(p.numel(), 8)  # 16B-aligned starts for bf16 and fp32 views
+        self.numel = off
+        self.padded = _round_up(max(off, 1), ALIGN * max(world, 1))
+        mk = alloc or (lambda n, dt: torch.zeros(n, dtype=dt, device=device))
+        self.w32 = mk(self.padded, torch.float32)
+        self.g32 = mk(self.padded, torch.float32)
+        self.slots = [torch.zeros(self.padded, dtype=torch.float32, device=device) for _ in range(n_slots)]
+        self.w16 = mk(self.padded, lowp) if lowp is not None else None
+        self.device = device
+
+    def view(self, flat: torch.Tensor, i: int) -> torch.Tensor:
+        p = self.params[i]
+        v = flat[self.offsets[i]: self.offsets[i] + p.numel()]
+        if p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last) and not p.is_contiguous():
+            k, c, r, s = p.shape
+            return v.view(k, r, s, c).permute(0, 3, 1, 2)  # physical KRSC, logical KCRS
+        return v.view(p.shape)
+
+
+class FusedReplica:
+    def __init__(self, model: nn.Module, dev, opt: Rule, world: int, rank: int, lowp: Optional[torch.dtype],
+                 alloc=None):
+        self.model, self.dev, self.opt = model, as_device(dev), opt
+        self.world, self.rank = world, rank
+        self.step_count = 0
+        self.group: Optional["FusedGroup"] = None
+        tdev = self.dev.torch_device
+        with device_ctx(self.dev):
+            self.arena = FlatArena(model, tdev, opt.n_slots, lowp, world, alloc)
+            a = self.arena
+            with torch.no_grad():
+                for i, p in enumerate(a.params):
+                    a.view(a.w32, i).copy_(p.detach().float())
+                    p.data = a.view(a.w32, i)       # the module now *is* the arena
+                    p.grad = a.view(a.g32, i)       # autograd accumulates in place
+                    p._gradbuf = p.grad             # native wgrad kernels write here
+                    if a.w16 is not None:
+                        p._lowp = a.view(a.w16, i)
+                if a.w16 is not None:
+                    a.w16.copy_(a.w32)
+
+    # ---- one training step on this replica
+    def forward_backward(self, x, y, loss: Callable) -> torch.Tensor:
+        with device_ctx(self.dev):
+            self.arena.g32.zero_()
+            for i, p in enumerate(self.arena.params):  # hooks may have replaced .grad
+                if p.grad is None or p.grad.data_ptr() != self.arena.view(self.arena.g32, i).data_ptr():
+                    p.grad = self.arena.view(self.arena.g32, i)
+            amp = self.arena.w16 is not None and self.dev.is_cuda
+            if amp and x.dtype == torch.float32:
+                x = x.to(self.arena.w16.dtype)
+            if amp:
+                with torch.autocast("cuda", dtype=self.arena.w16.dtype):
+                    out = self.model(x)
+                    l = loss(out, y)
+            else:
+                out = self.model(x)
+                l = loss(out, y)
+            l.backward()
+            return l.detach()
+
+    def reduce_and_update(self) -> None:
+        assert self.group is not None
+        self.step_count += 1
+        self.group.comm.allreduce_update(self)
+
+    def zero_grads(self) -> None:
+        self.arena.g32.zero_()
+
+    def step(self, x, y, loss: Callable, fused_update: bool = True):
+        l = self.forward_backward(x, y, loss)
+        if fused_update:
+            self.reduce_and_update()
+        return l
+
+    # ---- logical optimiser state in the reference's tree form
+    def state_tree(self) -> Tree:
+        a = self.arena
+        idx = {id(p): i for i, p in enumerate(a.params)}
+        t = self.step_count
+
+        def leaf(p):
+            if id(p) not in idx:
+                return None
+            i = idx[id(p)]
+            sl = [a.view(s, i).clone() for s in a.slots]
+            if self.opt.rule_id in (RULE_ADAM, RULE_ADAMW):
+                b1, b2 = self.opt.beta
+                return (sl[0], sl[1], (b1 ** (t + 1), b2 ** (t + 1)))
+            return sl[0] if sl else None
+
+        return _module_tree(self.model, leaf)
+
+    def load_state_tree(self, st: Tree, step_count: int = 0) -> None:
+        from ..tree import leaves
+
+        a = self.arena
+        vals = [v for _, v in leaves(_module_tree(self.model, lambda p: p))]
+        flat = [v for _, v in leaves(st)] if st is not None else []
+        self.step_count = step_count
+        # walk model params in order and copy moments in
+        it = iter(self._state_leaves(st))
+        for i, _p in enumerate(a.params):
+            s = next(it, None)
+            if s is None:
+                continue
+            if isinstance(s, tuple):
+                a.view(a.slots[0], i).copy_(s[0])
+                a.view(a.slots[1], i).copy_(s[1])
+            else:
+                a.view(a.slots[0], i).copy_(s)
+
+    def _state_leaves(self, st):
+        def rec(m, s):
+            for name, p in m.named_parameters(recurse=False):
+                if p.requires_grad:
+                    yield None if s is None else s.get(name)
+            for name, c in m.named_children():
+                yield from rec(c, None if s is None else s.get(name))
+
+        return rec(self.model, st)
+
+
+# =========================================================================== communicators
+class ThreadComm:
+    """Oracle communicator for threads of one process (CPU, or CUDA without the
+    extension): barrier, every replica averages all gradient arenas in rank order
+    (bit-identical on every replica), applies ``flat_step`` to its full arena."""
+
+    name = "thread"
+
+    def __init__(self, replicas: Sequence[FusedReplica]):
+        self.replicas = list(replicas)
+        n = len(self.replicas)
+        self._b1 = threading.Barrier(n) if n > 1 else None
+        self._b2 = threading.Barrier(n) if n > 1 else None
+
+    def allreduce_update(self, rep: FusedReplica) -> None:
+        if self._b1 is not None:
+            if rep.dev.is_cuda:
+                torch.cuda.synchronize(rep.dev.torch_device)
+            self._b1.wait()
+        a = rep.arena
+        acc = torch.zeros_like(a.g32)
+        for r in self.replicas:  # fixed order -> identical rounding everywhere
+            acc += r.arena.g32.to(a.device)
+        acc /= float(len(self.replicas))
+        flat_step(rep.opt, a.w32, acc, a.slots, rep.step_count)
+        if a.w16 is not None:
+            a.w16.copy_(a.w32)
+        if self._b2 is not None:
+            if rep.dev.is_cuda:
+                torch.cuda.synchronize(rep.dev.torch_device)
+            self._b2.wait()
+
+    def close(self):
+        pass
+
+
+class DistComm:
+    """``torch.distributed`` all-reduce + flat update (gloo on CPU; NCCL baseline on CUDA)."""
+
+    name = "dist"
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+
+    def allreduce_update(self, rep: FusedReplica) -> None:
+        a = rep.arena
+        if self.world > 1:
+            self.dist.all_reduce(a.g32, op=self.dist.ReduceOp.SUM, group=self.group)
+            a.g32.div_(float(self.world))
+        flat_step(rep.opt, a.w32, a.g32, a.slots, rep.step_count)
+        if a.w16 is not None:
+            a.w16.copy_(a.w32)
+
+    def close(self):
+        pass
+
+
+class FusedGroup:
+    def __init__(self, replicas: Sequence[FusedReplica], comm, loss=None):
+        self.replicas = list(replicas)
+        self.comm = comm
+        self.loss = loss
+        for r in self.replicas:
+            r.group = self
+
+    # ---- constructors
+    @staticmethod
+    def _lowp(dtype, devs) -> Optional[torch.dtype]:
+        if dtype is None:
+            return torch.bfloat16 if all(d.is_cuda for d in devs) else None
+        return None if dtype == torch.float32 else dtype
+
+    @classmethod
+    def for_threads(cls, models: Sequence[nn.Module], devs: Sequence, opt: Rule, loss=None, dtype=None,
+                    comm: str = "auto", **kw) -> "FusedGroup":
+        """Task mode: N replicas in this process."""
+        devs = [as_device(d) for d in devs]
+        lowp = cls._lowp(dtype, devs)
+        n = len(models)
+        use_native = comm == "native" or (comm == "auto" and all(d.is_cuda for d in devs) and _native_ok())
+        alloc = None
+        if use_native:
+            from .native_comm import NativeComm
+
+            reps = NativeComm.build_thread_replicas(models, devs, opt, lowp, **kw)
+            return cls(reps, reps[0]._native_comm, loss)
+        reps = [FusedReplica(m, d, opt, n, i, lowp, alloc) for i, (m, d) in enumerate(zip(models, devs))]
+        return cls(reps, ThreadComm(reps), loss)
+
+    @classmethod
+    def for_process(cls, model: nn.Module, dev, opt: Rule, loss=None, dtype=None, comm: str = "auto",
+                    group=None, **kw) -> "FusedGroup":
+        """Process mode: this process owns one replica; peers are other ranks of the
+        default (or given) ``torch.distributed`` group."""
+        import torch.distributed as dist
+
+        dev = as_device(dev)
+        if not dist.is_initialized():
+            backend = "nccl" if dev.is_cuda else "gloo"
+            dist.init_process_group(backend, device_id=dev.torch_device if dev.is_cuda else None)
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        lowp = cls._lowp(dtype, [dev])
+        use_native = comm == "native" or (comm == "auto" and dev.is_cuda and _native_ok())
+        if use_native:
+            from .native_comm import NativeComm
+
+            rep = NativeComm.build_process_replica(model, dev, opt, lowp, world, rank, group, **kw)
+            return cls([rep], rep._native_comm, loss)
+        rep = FusedReplica(model, dev, opt, world, rank, lowp)
+        # replicas must start identical (the reference copies one host model to every device)
+        if world > 1:
+            dist.broadcast(rep.arena.w32, src=0, group=group)
+            if rep.arena.w16 is not None:
+                rep.arena.w16.copy_(rep.arena.w32)
+        return cls([rep], DistComm(group), loss)
+
+    # ---- API used by task.train / process workers
+    def set_opt(self, opt: Rule) -> None:
+        for r in self.replicas:
+            r.opt = opt
+
+    def sync_to_modules(self) -> None:
+        """Make every module's fp32 parameters current (gathers owner shards when
+        the communicator keeps sharded masters)."""
+        if hasattr(self.comm, "gather_masters"):
+            self.comm.gather_masters(self.replicas)
+
+    def state_trees(self) -> Dict[Any, Tree]:
+        if hasattr(self.comm, "gather_slots"):
+            self.comm.gather_slots(self.replicas)
+        return {r.dev: r.state_tree() for r in self.replicas}
+
+    def close(self) -> None:
+        self.comm.close()
+
+
+def _native_ok() -> bool:
+    from .. import ops
+
+    return ops.native_available()

@@ -1,0 +1,141 @@
+"""Tracing / profiling helpers (the reference has none; the metric
+requires device timing as max over ranks).
+
+* ``nvtx_range`` — NVTX ranges per phase (load / fwd / bwd / allreduce+update).
+* ``DeviceTimer`` — CUDA-event timing on the launching stream.
+* ``PhaseTimes`` — accumulates per-phase device/host time for the step breakdown.
+* ``ClockSampler`` — samples ``nvidia-smi`` clocks/throttle reasons during a timed
+  region (bench contract: the ``clocks`` key).
+"""
+from __future__ import annotations
+
+import contextlib
+import statistics
+import subprocess
+import threading
+import time
+from collections import defaultdict
+from typing import Dict, List, Optional
+
+import torch
+
+
+@contextlib.contextmanager
+def nvtx_range(name: str):
+    if torch.cuda.is_available():
+        torch.cuda.nvtx.range_push(name)
+        try:
+            yield
+        finally:
+            torch.cuda.nvtx.range_pop()
+    else:
+        yield
+
+
+class DeviceTimer:
+    """CUDA events on the current stream; falls back to wall-clock on CPU."""
+
+    def __init__(self, device=None):
+        self.cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
+        self.device = device
+        if self.cuda:
+            self._a = torch.cuda.Event(enable_timing=True)
+            self._b = torch.cuda.Event(enable_timing=True)
+        self._t0 = 0.0
+        self._t1 = 0.0
+
+    def start(self):
+        if self.cuda:
+            self._a.record()
+        else:
+            self._t0 = time.perf_counter()
+
+    def stop(self):
+        if self.cuda:
+            self._b.record()
+        else:
+            self._t1 = time.perf_counter()
+
+    def elapsed_ms(self) -> float:
+        if self.cuda:
+            self._b.synchronize()
+            return self._a.elapsed_time(self._b)
+        return (self._t1 - self._t0) * 1e3
+
+
+class PhaseTimes:
+    def __init__(self):
+        self.ms: Dict[str, List[float]] = defaultdict(list)
+
+    @contextlib.contextmanager
+    def phase(self, name: str, device=None):
+        t = DeviceTimer(device)
+        with nvtx_range(name):
+            t.start()
+            yield
+            t.stop()
+        self.ms[name].append(t.elapsed_ms())
+
+    def summary(self) -> Dict[str, float]:
+        return {k: statistics.fmean(v) for k, v in self.ms.items() if v}
+
+
+class ClockSampler:
+    """Background ``nvidia-smi`` sampler (B200_PROFILING.md clocks line)."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0, period_ms: int = 100):
+        self.gpu_index = gpu_index
+        self.period_ms = period_ms
+        self._proc: Optional[subprocess.Popen] = None
+        self._lines: List[str] = []
+        self._thread: Optional[threading.Thread] = None
+
+    def start(self):
+        try:
+            self._proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-i", str(self.gpu_index), "-lms", str(self.period_ms)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self._proc = None
+            return self
+
+        def pump():
+            assert self._proc is not None and self._proc.stdout is not None
+            for line in self._proc.stdout:
+                self._lines.append(line.strip())
+
+        self._thread = threading.Thread(target=pump, daemon=True)
+        self._thread.start()
+        return self
+
+    def stop(self) -> Dict:
+        if self._proc is not None:
+            self._proc.terminate()  # exact PID we started
+            try:
+                self._proc.wait(timeout=2)
+            except Exception:
+                self._proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self._lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        # "under load": keep the upper half of samples by clock to drop idle ramp-up
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
+                "samples": len(sm)}
