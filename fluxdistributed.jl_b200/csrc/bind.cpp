@@ -1,0 +1,262 @@
+// Python bindings (the only translation unit that sees torch / pybind11).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <torch/extension.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fused_update.h"
+#include "igemm.h"
+#include "nn_kernels.h"
+#include "staging.h"
+
+const char* fd_last_error();
+long fd_launch_count();
+
+namespace {
+
+inline cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+inline void check(int rc, const char* what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + " failed: " + fd_last_error());
+}
+inline void want(const at::Tensor& t, at::ScalarType dt, const char* name) {
+  TORCH_CHECK(t.is_cuda(), name, " must be a CUDA tensor");
+  TORCH_CHECK(t.scalar_type() == dt, name, " has wrong dtype");
+}
+inline const void* optptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
+inline float* optf(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+
+// ---------------------------------------------------------------- fused all-reduce + update plan
+struct FusedPlan {
+  FusedArgs a{};
+  int grid = 1;
+  int device = 0;
+
+  FusedPlan(int world, int rank, int rule, int mode, int use_nvls, long n, long fp32_bcast_from,
+            std::vector<int64_t> g, int64_t w32, int64_t s0, int64_t s1, std::vector<int64_t> wout32,
+            std::vector<int64_t> wout16, std::vector<int64_t> flags, int64_t epoch, int64_t step_dev,
+            int64_t done_ctr, int64_t status, int64_t mc_g, int64_t mc_w32, int64_t mc_w16, int max_grid,
+            int device_) {
+    TORCH_CHECK(world >= 1 && world <= FD_MAX_WORLD, "world must be in [1, 8]");
+    TORCH_CHECK(n % (4 * world) == 0, "bucket length must be a multiple of 4*world");
+    a.world = world; a.rank = rank; a.rule = rule; a.mode = mode; a.use_nvls = use_nvls;
+    a.n = n; a.fp32_bcast_from = fp32_bcast_from; a.grad_scale = 1.f;
+    for (int i = 0; i < FD_MAX_WORLD; ++i) {
+      a.g[i] = i < (int)g.size() ? reinterpret_cast<const float*>(g[i]) : nullptr;
+      a.wout32[i] = i < (int)wout32.size() ? reinterpret_cast<float*>(wout32[i]) : nullptr;
+      a.wout16[i] = i < (int)wout16.size() ? reinterpret_cast<__nv_bfloat16*>(wout16[i]) : nullptr;
+      a.flags[i] = i < (int)flags.size() ? reinterpret_cast<uint32_t*>(flags[i]) : nullptr;
+    }
+    a.w32 = reinterpret_cast<float*>(w32);
+    a.s0 = reinterpret_cast<float*>(s0);
+    a.s1 = reinterpret_cast<float*>(s1);
+    a.epoch = reinterpret_cast<uint32_t*>(epoch);
+    a.step_dev = reinterpret_cast<int*>(step_dev);
+    a.done_ctr = reinterpret_cast<unsigned*>(done_ctr);
+    a.status = reinterpret_cast<int*>(status);
+    a.max_spins = 1ll << 26;
+    a.mc_g = reinterpret_cast<const float*>(mc_g);
+    a.mc_w32 = reinterpret_cast<float*>(mc_w32);
+    a.mc_w16 = reinterpret_cast<__nv_bfloat16*>(mc_w16);
+    grid = fd_fused_update_grid(n, world, mode, max_grid);
+    device = device_;
+  }
+  void set_hyper(std::vector<double> h, double grad_scale) {
+    for (size_t i = 0; i < 8; ++i) a.h[i] = i < h.size() ? (float)h[i] : 0.f;
+    a.grad_scale = (float)grad_scale;
+  }
+  void set_max_spins(long long s) { a.max_spins = s; }
+  void launch() {
+    c10::cuda::CUDAGuard guard(device);
+    check(fd_fused_update_launch(a, grid, cur_stream()), "fused_update");
+  }
+};
+
+void gather_shards(at::Tensor dst, at::Tensor src_ptrs_dev, int world, int rank) {
+  want(dst, at::kFloat, "dst");
+  c10::cuda::CUDAGuard guard(dst.device());
+  check(fd_gather_shards(dst.data_ptr<float>(), reinterpret_cast<const float* const*>(src_ptrs_dev.data_ptr()), world,
+                         rank, dst.numel(), cur_stream()),
+        "gather_shards");
+}
+
+// ---------------------------------------------------------------- tensor-core GEMM / conv
+void gemm_nt(at::Tensor A, at::Tensor B, at::Tensor D) {
+  want(A, at::kBFloat16, "A");
+  want(B, at::kBFloat16, "B");
+  TORCH_CHECK(A.is_contiguous() && B.is_contiguous() && D.is_contiguous(), "gemm_nt wants contiguous operands");
+  c10::cuda::CUDAGuard guard(A.device());
+  check(fd_gemm_nt(A.data_ptr(), B.data_ptr(), D.data_ptr(), (int)A.size(0), (int)B.size(0), (int)A.size(1),
+                   D.scalar_type() == at::kFloat, cur_stream()),
+        "gemm_nt");
+}
+// x: [N,H,W,C] bf16 (physical NHWC), w: [K,R,S,C] bf16, y: [N,P,Q,K] bf16
+void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad) {
+  want(x, at::kBFloat16, "x");
+  want(w, at::kBFloat16, "w");
+  want(y, at::kBFloat16, "y");
+  c10::cuda::CUDAGuard guard(x.device());
+  check(fd_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                      (int)x.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
+        "conv_fprop");
+}
+void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad) {
+  want(dy, at::kBFloat16, "dy");
+  want(w, at::kBFloat16, "w");
+  want(dx, at::kBFloat16, "dx");
+  c10::cuda::CUDAGuard guard(dy.device());
+  check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+                      (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
+        "conv_dgrad");
+}
+void conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor dw, int stride, int pad, int splits, bool accumulate) {
+  want(dy, at::kBFloat16, "dy");
+  want(x, at::kBFloat16, "x");
+  want(dw, at::kFloat, "dw");
+  c10::cuda::CUDAGuard guard(dy.device());
+  check(fd_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                      (int)x.size(3), (int)dw.size(0), (int)dw.size(1), (int)dw.size(2), stride, pad, splits,
+                      accumulate ? 1 : 0, cur_stream()),
+        "conv_wgrad");
+}
+
+// ---------------------------------------------------------------- bandwidth-bound kernels
+void bn_stats(at::Tensor y, at::Tensor sum, at::Tensor sumsq) {
+  want(y, at::kBFloat16, "y");
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)sum.numel();
+  check(fd_bn_stats(y.data_ptr(), sum.data_ptr<float>(), sumsq.data_ptr<float>(), y.numel() / C, C, cur_stream()),
+        "bn_stats");
+}
+void bn_apply(at::Tensor y, c10::optional<at::Tensor> res, at::Tensor out, at::Tensor sum, at::Tensor sumsq,
+              at::Tensor gamma, at::Tensor beta, c10::optional<at::Tensor> run_mean,
+              c10::optional<at::Tensor> run_var, c10::optional<at::Tensor> save_mean,
+              c10::optional<at::Tensor> save_rstd, double eps, double momentum, bool training, bool relu) {
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)gamma.numel();
+  check(fd_bn_apply(y.data_ptr(), optptr(res), out.data_ptr(), sum.data_ptr<float>(), sumsq.data_ptr<float>(),
+                    gamma.data_ptr<float>(), beta.data_ptr<float>(), optf(run_mean), optf(run_var), optf(save_mean),
+                    optf(save_rstd), y.numel() / C, C, (float)eps, (float)momentum, training, relu, cur_stream()),
+        "bn_apply");
+}
+void bn_bwd(at::Tensor dout, at::Tensor y, c10::optional<at::Tensor> out, at::Tensor mean, at::Tensor rstd,
+            at::Tensor gamma, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy, c10::optional<at::Tensor> dres,
+            bool relu) {
+  c10::cuda::CUDAGuard guard(y.device());
+  const int C = (int)gamma.numel();
+  check(fd_bn_bwd(dout.data_ptr(), y.data_ptr(), optptr(out), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                  gamma.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr(),
+                  dres.has_value() ? dres->data_ptr() : nullptr, y.numel() / C, C, relu, cur_stream()),
+        "bn_bwd");
+}
+void maxpool_fwd(at::Tensor x, at::Tensor out, int k, int stride, int pad) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check(fd_maxpool_fwd(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3), k,
+                       stride, pad, cur_stream()),
+        "maxpool_fwd");
+}
+void maxpool_bwd(at::Tensor x, at::Tensor out, at::Tensor dout, at::Tensor dx, int k, int stride, int pad) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check(fd_maxpool_bwd(x.data_ptr(), out.data_ptr(), dout.data_ptr(), dx.data_ptr(), (int)x.size(0), (int)x.size(1),
+                       (int)x.size(2), (int)x.size(3), k, stride, pad, cur_stream()),
+        "maxpool_bwd");
+}
+void gap_fwd(at::Tensor x, at::Tensor out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  check(fd_gap_fwd(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)(x.size(1) * x.size(2)), (int)x.size(3),
+                   cur_stream()),
+        "gap_fwd");
+}
+void gap_bwd(at::Tensor dout, at::Tensor dx) {
+  c10::cuda::CUDAGuard guard(dx.device());
+  check(fd_gap_bwd(dout.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)(dx.size(1) * dx.size(2)), (int)dx.size(3),
+                   cur_stream()),
+        "gap_bwd");
+}
+void softmax_ce(at::Tensor logits, at::Tensor labels, at::Tensor dlogits, at::Tensor row_loss, at::Tensor loss,
+                at::Tensor counter, double scale) {
+  want(labels, at::kLong, "labels");
+  c10::cuda::CUDAGuard guard(logits.device());
+  check(fd_softmax_ce(logits.data_ptr(), reinterpret_cast<const long long*>(labels.data_ptr<int64_t>()),
+                      dlogits.data_ptr(), row_loss.data_ptr<float>(), loss.data_ptr<float>(),
+                      reinterpret_cast<unsigned*>(counter.data_ptr()), (int)logits.size(0), (int)logits.size(1),
+                      logits.stride(0), (float)scale, logits.scalar_type() == at::kBFloat16, cur_stream()),
+        "softmax_ce");
+}
+void normalize_u8(at::Tensor in, at::Tensor out, std::vector<double> mean, std::vector<double> stdv) {
+  c10::cuda::CUDAGuard guard(in.device());
+  float m[3] = {(float)mean[0], (float)mean[1], (float)mean[2]}, s[3] = {(float)stdv[0], (float)stdv[1], (float)stdv[2]};
+  check(fd_normalize_u8(in.data_ptr(), out.data_ptr(), in.numel() / 3, (int)out.size(-1), m, s, cur_stream()),
+        "normalize_u8");
+}
+void cast_f32_bf16(at::Tensor in, at::Tensor out) {
+  c10::cuda::CUDAGuard guard(in.device());
+  check(fd_cast_f32_bf16(in.data_ptr<float>(), out.data_ptr(), in.numel(), cur_stream()), "cast");
+}
+void small_gemm(at::Tensor A, at::Tensor B, at::Tensor C, int M, int N, int K, long sam, long sak, long sbk, long sbn) {
+  c10::cuda::CUDAGuard guard(A.device());
+  const bool f32 = C.scalar_type() == at::kFloat;
+  check(fd_small_gemm(A.data_ptr(), B.data_ptr(), f32 ? C.data_ptr<float>() : nullptr, f32 ? nullptr : C.data_ptr(), M,
+                      N, K, sam, sak, sbk, sbn, C.stride(0), cur_stream()),
+        "small_gemm");
+}
+void bias_add(at::Tensor y, at::Tensor bias) {
+  c10::cuda::CUDAGuard guard(y.device());
+  check(fd_bias_add(y.data_ptr(), bias.data_ptr<float>(), (int)y.size(0), (int)y.size(1), cur_stream()), "bias_add");
+}
+void colsum(at::Tensor d, at::Tensor out) {
+  c10::cuda::CUDAGuard guard(d.device());
+  check(fd_colsum(d.data_ptr(), out.data_ptr<float>(), (int)d.size(0), (int)d.size(1), cur_stream()), "colsum");
+}
+
+void enable_peer_access(int dev, int peer) {
+  c10::cuda::CUDAGuard guard(dev);
+  int can = 0;
+  cudaDeviceCanAccessPeer(&can, dev, peer);
+  TORCH_CHECK(can, "device ", dev, " cannot access peer ", peer);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return;
+  }
+  TORCH_CHECK(e == cudaSuccess, "cudaDeviceEnablePeerAccess: ", cudaGetErrorString(e));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "fluxdist sm_100a kernels";
+  m.attr("arch") = "sm_100a";
+  py::class_<FusedPlan>(m, "FusedPlan")
+      .def(py::init<int, int, int, int, int, long, long, std::vector<int64_t>, int64_t, int64_t, int64_t,
+                    std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t,
+                    int64_t, int64_t, int64_t, int64_t, int, int>())
+      .def("set_hyper", &FusedPlan::set_hyper)
+      .def("set_max_spins", &FusedPlan::set_max_spins)
+      .def("launch", &FusedPlan::launch)
+      .def_readonly("grid", &FusedPlan::grid);
+  m.def("gather_shards", &gather_shards);
+  m.def("gemm_nt", &gemm_nt);
+  m.def("conv_fprop", &conv_fprop);
+  m.def("conv_dgrad", &conv_dgrad);
+  m.def("conv_wgrad", &conv_wgrad);
+  m.def("bn_stats", &bn_stats);
+  m.def("bn_apply", &bn_apply);
+  m.def("bn_bwd", &bn_bwd);
+  m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("gap_fwd", &gap_fwd);
+  m.def("gap_bwd", &gap_bwd);
+  m.def("softmax_ce", &softmax_ce);
+  m.def("normalize_u8", &normalize_u8);
+  m.def("cast_f32_bf16", &cast_f32_bf16);
+  m.def("small_gemm", &small_gemm);
+  m.def("bias_add", &bias_add);
+  m.def("colsum", &colsum);
+  m.def("enable_peer_access", &enable_peer_access);
+  m.def("num_sms", &fd_num_sms);
+  m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
+  fd_bind_staging(m);
+}

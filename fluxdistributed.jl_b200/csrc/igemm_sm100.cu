@@ -1,0 +1,514 @@
+// Implicit-GEMM convolution and GEMM on 5th-gen tensor cores (sm_100a).
+//
+// One persistent, warp-specialised kernel template serves
+//   GEMM  : D[M,N] = A[M,K] * B[N,K]^T                       (FC head, 1x1 convs)
+//   FPROP : Y[n,p,q,k]  = sum_{r,s,c} X[n,p*st+r-pad,q*st+s-pad,c] W[k,r,s,c]        
+//   DGRAD : dX[n,h,w,c] = sum_{r,s,k} dY[n,h+pad-r,w+pad-s,k] W[k,r,s,c]   (stride 1)  
+//   WGRAD : dW[k,r,s,c] = sum_{n,p,q} dY[n,p,q,k] X[n,p*st+r-pad,q*st+s-pad,c]        
+// with bf16 operands and fp32 accumulation:
+//   * operands are staged in shared memory by TMA — activations through *im2col-mode* tensor
+//     maps (cp.async.bulk.tensor.4d...im2col) so padding/stride/halo handling is done by the
+//     copy engine, weights/plain matrices through tiled maps — into 128B-swizzled tiles;
+//   * one elected thread issues tcgen05.mma (cta_group::1, M=128, N=64|128, K=16) reading the
+//     tiles through UMMA shared-memory descriptors; accumulators live in TMEM, double-buffered
+//     so the epilogue of tile i overlaps the main loop of tile i+1;
+//   * four epilogue warps pull the accumulator out with tcgen05.ld (32 lanes x 32 columns),
+//     convert and store (bf16 NHWC rows, or fp32 red.add for split-K wgrad).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+#include <string>
+#include <cstring>
+
+#include "common.cuh"
+#include "igemm.h"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // bf16 elements per k-block = one 128B swizzle row
+constexpr int kThreads = 192;
+
+enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_WGRAD = 3 };
+
+struct KParams {
+  int mode;
+  int M, N;           // GEMM extents seen by the epilogue (rows, cols)
+  int num_kb;         // k-blocks per tile (per split for wgrad)
+  int m_tiles, n_tiles, splits;
+  // conv geometry
+  int PQ, Q;          // output (M-space) image extent for m -> (n,p,q)
+  int stride;         // traversal stride of the im2col walk
+  int lower_w, lower_h;
+  int S, C_chunks;    // taps per filter row; 64-channel chunks per tap (of the reduction operand)
+  int Ctot;           // channels per tap in the weight matrix row (R*S*C row => column = tap*Ctot + c)
+  int flip, R;        // dgrad: use tap (R-1-r, S-1-s) offsets
+  // wgrad
+  int taps;           // R*S
+  int kb_total;       // total pixel k-blocks
+  // output
+  void* out;
+  long ldo;           // row stride in elements
+  int out_fp32;       // 1: float output (store or atomic add)
+  int out_atomic;
+};
+
+template <int BN, int MODE>
+struct Cfg {
+  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;  // 8/16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM_BYTES = kStages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
+};
+
+template <int BN, int MODE>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams P) {
+  using C = Cfg<BN, MODE>;
+  constexpr int kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + kStages * C::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int total_tiles = P.m_tiles * P.n_tiles * P.splits;
+
+  if (warp == 0) {
+    // ===================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int split = t / (P.m_tiles * P.n_tiles);
+        int rem = t - split * (P.m_tiles * P.n_tiles);
+        const int mt = rem / P.n_tiles, nt = rem % P.n_tiles;
+        const int m0 = mt * BM, n0 = nt * BN;
+        // base pixel of this tile (conv modes)
+        int bn = 0, bh = 0, bw = 0;
+        if (MODE == MODE_FPROP || MODE == MODE_DGRAD) {
+          bn = m0 / P.PQ;
+          int r2 = m0 - bn * P.PQ;
+          int p = r2 / P.Q, q = r2 - p * P.Q;
+          bh = P.lower_h + p * P.stride;
+          bw = P.lower_w + q * P.stride;
+        }
+        int kb_begin = 0, kb_end = P.num_kb;
+        int tap = 0;
+        if (MODE == MODE_WGRAD) {
+          // n-tile index enumerates (tap, c-chunk); split enumerates pixel ranges
+          tap = nt / P.C_chunks;
+          kb_begin = (int)(((long)P.kb_total * split) / P.splits);
+          kb_end = (int)(((long)P.kb_total * (split + 1)) / P.splits);
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* a = smemA + stage * C::A_BYTES;
+          uint8_t* b = smemB + stage * C::B_BYTES;
+          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          if (MODE == MODE_GEMM) {
+            tma_load_2d(a, &mapA, &full[stage], kb * BK, m0);
+            tma_load_2d(b, &mapB, &full[stage], kb * BK, n0);
+          } else if (MODE == MODE_FPROP) {
+            const int tp = kb / P.C_chunks, cc = kb - tp * P.C_chunks;
+            const int r = tp / P.S, s = tp - r * P.S;
+            tma_load_im2col_4d(a, &mapA, &full[stage], cc * BK, bw, bh, bn, (uint16_t)s, (uint16_t)r);
+            tma_load_2d(b, &mapB, &full[stage], tp * P.Ctot + cc * BK, n0);
+          } else if (MODE == MODE_DGRAD) {
+            // reduction over (tap, k-chunk); A = im2col(dY) with flipped taps, B = W[k, (r,s,c)] (N-major)
+            const int tp = kb / P.C_chunks, kc = kb - tp * P.C_chunks;
+            const int r = tp / P.S, s = tp - r * P.S;
+            tma_load_im2col_4d(a, &mapA, &full[stage], kc * BK, bw, bh, bn, (uint16_t)(P.S - 1 - s),
+                               (uint16_t)(P.R - 1 - r));
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(b + j * (BK * 128), &mapB, &full[stage], tp * P.Ctot + n0 + j * 64, kc * BK);
+          } else {  // WGRAD: A = dY[pixels, k] (M-major), B = im2col(X)[pixels, c] (N-major), both 64-pixel k-blocks
+            const int cc = nt - tap * P.C_chunks;
+            const int r = tap / P.S, s = tap - r * P.S;
+            const int pix0 = kb * BK;
+            int pn = pix0 / P.PQ;
+            int r2 = pix0 - pn * P.PQ;
+            int p = r2 / P.Q, q = r2 - p * P.Q;
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(a + j * (BK * 128), &mapA, &full[stage], m0 + j * 64, pix0);
+            tma_load_im2col_4d(b, &mapB, &full[stage], cc * BN, P.lower_w + q * P.stride, P.lower_h + p * P.stride, pn,
+                               (uint16_t)s, (uint16_t)r);
+          }
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================== MMA issuer
+    constexpr bool A_MN = (MODE == MODE_WGRAD);
+    constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_WGRAD);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int kb_count = P.num_kb;
+      if (MODE == MODE_WGRAD) {
+        int split = t / (P.m_tiles * P.n_tiles);
+        int b0 = (int)(((long)P.kb_total * split) / P.splits);
+        int b1 = (int)(((long)P.kb_total * (split + 1)) / P.splits);
+        kb_count = b1 - b0;
+      }
+      mbar_wait(&tempty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < kb_count; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(smemA + stage * C::A_BYTES);
+          const uint32_t b_addr = smem_u32(smemB + stage * C::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major SW128: 8-row groups 1024B apart, advance 32B per UMMA_K inside the swizzle row.
+            // MN-major SW128: tile is [k rows][64 mn elems]; 8-k groups 1024B apart (SBO), 64-mn blocks
+            // BK*128B apart (LBO); advance 16 rows = 2048B per UMMA_K.
+            const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, BK * 128, 1024, UMMA_LAYOUT_SW128)
+                                     : umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, BK * 128, 1024, UMMA_LAYOUT_SW128)
+                                     : umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);                         // smem slot free once these MMAs retire
+          if (kb == kb_count - 1) umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (kb_count == 0 && lane == 0) umma_commit(&tfull[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  } else {
+    // ===================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int split = t / (P.m_tiles * P.n_tiles);
+      int rem = t - split * (P.m_tiles * P.n_tiles);
+      const int mt = rem / P.n_tiles, nt = rem % P.n_tiles;
+      const int m0 = mt * BM;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      bool has_k = true;
+      if (MODE == MODE_WGRAD) {
+        int b0 = (int)(((long)P.kb_total * split) / P.splits);
+        int b1 = (int)(((long)P.kb_total * (split + 1)) / P.splits);
+        has_k = b1 > b0;
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
+        tmem_ld_wait();
+        if (row < P.M && has_k) {
+          if (MODE == MODE_WGRAD) {
+            // row = output channel k; columns = (tap, c) block: out[k][tap*Ctot + cc*BN + c]
+            const int tap = nt / P.C_chunks, cc = nt - tap * P.C_chunks;
+            float* o = reinterpret_cast<float*>(P.out) + (long)row * P.ldo + (long)tap * P.Ctot + cc * BN + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (P.out_atomic)
+                atomicAdd(o + j, __uint_as_float(v[j]));
+              else
+                o[j] = __uint_as_float(v[j]);
+            }
+          } else {
+            const int col0 = nt * BN + c0;
+            if (P.out_fp32) {
+              float* o = reinterpret_cast<float*>(P.out) + (long)row * P.ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                if (col0 + j + 4 <= P.N)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(P.out) + (long)row * P.ldo + col0;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j + 8 <= P.N) {
+                  uint4 u;
+                  u.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                  u.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                  u.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                  u.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                  *reinterpret_cast<uint4*>(o + j) = u;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled g_encodeTiled = nullptr;
+PFN_encodeIm2col g_encodeIm2col = nullptr;
+int g_num_sms = 0;
+std::mutex g_mu;
+
+int ensure_driver() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_encodeTiled && g_encodeIm2col) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  FD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+  g_encodeTiled = (PFN_encodeTiled)f;
+  FD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f, cudaEnableDefault, &q));
+  g_encodeIm2col = (PFN_encodeIm2col)f;
+  int dev = 0;
+  FD_CUDA_CHECK(cudaGetDevice(&dev));
+  FD_CUDA_CHECK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  if (!g_encodeTiled || !g_encodeIm2col) {
+    fd_set_error("cuTensorMapEncode* entry points unavailable", __FILE__, __LINE__);
+    return -1;
+  }
+  return 0;
+}
+
+// 2D tiled map over a row-major [rows, cols] bf16 matrix; box = {64 cols (128B), box_rows}
+int make_map_2d(CUtensorMap* m, const void* base, long rows, long cols, long ld_elems, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("cuTensorMapEncodeTiled failed", __FILE__, (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+// im2col map over an NHWC bf16 tensor; box = {64 channels, pixels}
+int make_map_im2col(CUtensorMap* m, const void* base, int N, int H, int W, int Cc, int lower_w, int lower_h,
+                    int upper_w, int upper_h, int stride, int pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
+  int lower[2] = {lower_w, lower_h};
+  int upper[2] = {upper_w, upper_h};
+  cuuint32_t es[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encodeIm2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                              upper, 64, (cuuint32_t)pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("cuTensorMapEncodeIm2col failed", __FILE__, (int)r);
+    return -1;
+  }
+  // driver workaround carried by CUTLASS (copy_traits_sm90_im2col.hpp): small tensors need bit 21 of the
+  // second descriptor word cleared on drivers <= 13.1
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (long)N * H * W * Cc * 2 < 131072) reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  return 0;
+}
+
+template <int BN, int MODE>
+int launch(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStream_t s) {
+  using C = Cfg<BN, MODE>;
+  static bool attr_set[16] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 15]) {
+    FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set[dev & 15] = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles * p.splits;
+  int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  if (grid < 1) grid = 1;
+  igemm_kernel<BN, MODE><<<grid, kThreads, C::SMEM_BYTES, s>>>(a, b, p);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+}  // namespace
+
+int fd_num_sms() { return g_num_sms; }
+
+int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s) {
+  if (ensure_driver()) return -1;
+  if (K % 64) {
+    fd_set_error("gemm_nt: K must be a multiple of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  CUtensorMap ma, mb;
+  const int bn = (N <= 64) ? 64 : 128;
+  if (make_map_2d(&ma, A, M, K, K, BM) || make_map_2d(&mb, B, N, K, K, bn)) return -1;
+  KParams p{};
+  p.mode = MODE_GEMM;
+  p.M = M; p.N = N;
+  p.num_kb = K / 64;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.splits = 1;
+  p.out = D; p.ldo = N; p.out_fp32 = out_fp32;
+  return bn == 64 ? launch<64, MODE_GEMM>(ma, mb, p, s) : launch<128, MODE_GEMM>(ma, mb, p, s);
+}
+
+int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
+                  int pad, cudaStream_t s) {
+  if (ensure_driver()) return -1;
+  if (C % 64 || K % 64) {
+    fd_set_error("conv_fprop: C and K must be multiples of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  const int P_ = (H + 2 * pad - R) / stride + 1, Q_ = (W + 2 * pad - S) / stride + 1;
+  const int bn = (K % 128 == 0) ? 128 : 64;
+  CUtensorMap ma, mb;
+  // bounding box of base pixels: [-pad, dim-1 + pad-(R-1)] (CUTLASS compute_{lower,upper}_corner_whd, fprop)
+  if (make_map_im2col(&ma, x, N, H, W, C, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, BM)) return -1;
+  if (make_map_2d(&mb, w, K, (long)R * S * C, (long)R * S * C, bn)) return -1;
+  KParams p{};
+  p.mode = MODE_FPROP;
+  p.M = N * P_ * Q_; p.N = K;
+  p.num_kb = R * S * (C / 64);
+  p.m_tiles = (p.M + BM - 1) / BM;
+  p.n_tiles = K / bn;
+  p.splits = 1;
+  p.PQ = P_ * Q_; p.Q = Q_; p.stride = stride; p.lower_w = -pad; p.lower_h = -pad;
+  p.S = S; p.R = R; p.C_chunks = C / 64; p.Ctot = C;
+  p.out = y; p.ldo = K; p.out_fp32 = 0;
+  return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
+}
+
+int fd_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int R, int S, int pad,
+                  cudaStream_t s) {
+  // stride-1 data gradient: dx[N,H,W,C] from dy[N,P,Q,K]; P = H + 2pad - R + 1
+  if (ensure_driver()) return -1;
+  if (C % 64 || K % 64) {
+    fd_set_error("conv_dgrad: C and K must be multiples of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  const int P_ = H + 2 * pad - R + 1, Q_ = W + 2 * pad - S + 1;
+  const int bn = (C % 128 == 0) ? 128 : 64;
+  CUtensorMap ma, mb;
+  // CUTLASS dgrad corners: lower = pad-(S-1), upper = pad-(S-1) + (W - Q)
+  if (make_map_im2col(&ma, dy, N, P_, Q_, K, pad - (S - 1), pad - (R - 1), pad - (S - 1) + (W - Q_),
+                      pad - (R - 1) + (H - P_), 1, BM))
+    return -1;
+  if (make_map_2d(&mb, w, K, (long)R * S * C, (long)R * S * C, 64)) return -1;
+  KParams p{};
+  p.mode = MODE_DGRAD;
+  p.M = N * H * W; p.N = C;
+  p.num_kb = R * S * (K / 64);
+  p.m_tiles = (p.M + BM - 1) / BM;
+  p.n_tiles = C / bn;
+  p.splits = 1;
+  p.PQ = H * W; p.Q = W; p.stride = 1; p.lower_w = pad - (S - 1); p.lower_h = pad - (R - 1);
+  p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
+  p.out = dx; p.ldo = C; p.out_fp32 = 0;
+  return bn == 64 ? launch<64, MODE_DGRAD>(ma, mb, p, s) : launch<128, MODE_DGRAD>(ma, mb, p, s);
+}
+
+int fd_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int R, int S,
+                  int stride, int pad, int splits, int accumulate, cudaStream_t s) {
+  // dw[K, R, S, C] (fp32) += sum over pixels; rows (M) = K output channels, columns = (tap, c)
+  if (ensure_driver()) return -1;
+  if (C % 64 || K % 64) {
+    fd_set_error("conv_wgrad: C and K must be multiples of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  const int P_ = (H + 2 * pad - R) / stride + 1, Q_ = (W + 2 * pad - S) / stride + 1;
+  const long pixels = (long)N * P_ * Q_;
+  const int bn = (C % 128 == 0) ? 128 : 64;
+  CUtensorMap ma, mb;
+  if (make_map_2d(&ma, dy, pixels, K, K, BK)) return -1;                       // box {64 k, 64 pixels}
+  // the im2col box has 64 channels; for bn=128 the kernel would need two boxes -> keep bn=64 boxes per load
+  if (make_map_im2col(&mb, x, N, H, W, C, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, BK)) return -1;
+  KParams p{};
+  p.mode = MODE_WGRAD;
+  p.M = K; p.N = R * S * C;
+  p.taps = R * S;
+  p.kb_total = (int)((pixels + BK - 1) / BK);
+  p.m_tiles = (K + BM - 1) / BM;  // K=64: the upper half of the M=128 tile is TMA zero-fill
+  p.C_chunks = C / 64;
+  p.n_tiles = R * S * p.C_chunks;
+  if (splits < 1) {
+    int base = p.m_tiles * p.n_tiles;
+    splits = (2 * g_num_sms + base - 1) / base;
+    if (splits > p.kb_total) splits = p.kb_total;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  p.num_kb = 0;
+  p.PQ = P_ * Q_; p.Q = Q_; p.stride = stride; p.lower_w = -pad; p.lower_h = -pad;
+  p.S = S; p.R = R; p.Ctot = C;
+  p.out = dw; p.ldo = (long)R * S * C; p.out_fp32 = 1; p.out_atomic = (splits > 1 || accumulate) ? 1 : 0;
+  (void)bn;
+  return launch<64, MODE_WGRAD>(ma, mb, p, s);
+}

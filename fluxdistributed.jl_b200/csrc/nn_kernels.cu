@@ -1,0 +1,619 @@
+// Bandwidth-bound NHWC bf16 kernels of the ResNet/CIFAR path:
+// BatchNorm statistics / apply(+residual,+ReLU) / backward, max-pool, global-average-pool,
+// fused softmax-cross-entropy (loss + dlogits in one pass), uint8 -> bf16 input normalisation.
+// All use 16-byte vector accesses along the channel (innermost) dimension and fp32 arithmetic.
+#include "common.cuh"
+#include "nn_kernels.h"
+
+namespace {
+
+struct alignas(16) V8 {
+  uint32_t u[4];
+};
+FD_DEVINL void unpack8(const V8& v, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = unpack_bf16x2(v.u[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+FD_DEVINL V8 pack8(const float* f) {
+  V8 v;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+FD_DEVINL V8 ldg8(const bf16* p) { return *reinterpret_cast<const V8*>(p); }
+FD_DEVINL void stg8(bf16* p, const V8& v) { *reinterpret_cast<V8*>(p) = v; }
+
+// ---------------------------------------------------------------------------------------------
+// BN statistics: per-channel sum and sum of squares over M rows of y[M, C].
+// Block = 256 threads arranged as (256 / (C/8)) row-lanes x (C/8) channel-vectors.
+// ---------------------------------------------------------------------------------------------
+template <int NQ>  // number of quantities reduced per channel (2: sum,sumsq)
+FD_DEVINL void block_channel_reduce(float (*acc)[8], int C8, int cv, int rl, int RL, float* smem, float* out0,
+                                    float* out1) {
+  // smem layout [RL][C8*8][NQ]
+  const int Cc = C8 * 8;
+  if (rl < RL) {
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[(rl * Cc + cv * 8 + j) * NQ + q] = acc[q][j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cc * NQ; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < RL; ++r) s += smem[r * Cc * NQ + c];
+    const int ch = c / NQ, q = c % NQ;
+    atomicAdd((q == 0 ? out0 : out1) + ch, s);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ y, float* __restrict__ sum,
+                                                       float* __restrict__ sumsq, long M, int C) {
+  extern __shared__ float smem[];
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (rl < RL) {
+    for (long r = (long)blockIdx.x * RL + rl; r < M; r += (long)gridDim.x * RL) {
+      float f[8];
+      unpack8(ldg8(y + r * C + cv * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] += f[j] * f[j];
+      }
+    }
+  }
+  block_channel_reduce<2>(acc, C8, cv, rl, RL, smem, sum, sumsq);
+}
+
+// BN apply: out = relu( (y-mean)*rstd*gamma + beta (+ residual) ).  mean/rstd derived from sum/sumsq
+// (training) or running stats (eval). Block 0 also emits saved mean/rstd and updates running stats.
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* __restrict__ out,
+                const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ run_mean, float* __restrict__ run_var,
+                float* __restrict__ save_mean, float* __restrict__ save_rstd, long M, int C, float eps,
+                float momentum, int training, int relu) {
+  extern __shared__ float smem[];  // scale[C], shift[C]
+  float* sc = smem;
+  float* sh = smem + C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, var;
+    if (training) {
+      mean = sum[c] * invM;
+      var = fmaxf(sumsq[c] * invM - mean * mean, 0.f);
+    } else {
+      mean = run_mean[c];
+      var = run_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma[c];
+    sc[c] = g * rstd;
+    sh[c] = beta[c] - mean * g * rstd;
+    if (blockIdx.x == 0) {
+      if (save_mean) save_mean[c] = mean;
+      if (save_rstd) save_rstd[c] = rstd;
+      if (training && run_mean) {
+        const float unbiased = var * ((float)M / fmaxf((float)M - 1.f, 1.f));
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const int C8 = C / 8;
+  const long total = M * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    float f[8], r[8];
+    unpack8(ldg8(y + i * 8), f);
+    if (res) unpack8(ldg8(res + i * 8), r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = f[j] * sc[cv * 8 + j] + sh[cv * 8 + j];
+      if (res) v += r[j];
+      if (relu) v = fmaxf(v, 0.f);
+      f[j] = v;
+    }
+    stg8(out + i * 8, pack8(f));
+  }
+}
+
+// BN backward pass 1: dgamma[c] = sum dz*xhat, dbeta[c] = sum dz, with dz = dout * (out > 0) if relu
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, long M, int C, int relu) {
+  extern __shared__ float smem[];
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
+  float acc[2][8];
+  float mu[8], rs[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = 0.f;
+    mu[j] = mean[cv * 8 + j];
+    rs[j] = rstd[cv * 8 + j];
+  }
+  if (rl < RL) {
+    for (long r = (long)blockIdx.x * RL + rl; r < M; r += (long)gridDim.x * RL) {
+      float d[8], yy[8], o[8];
+      unpack8(ldg8(dout + r * C + cv * 8), d);
+      unpack8(ldg8(y + r * C + cv * 8), yy);
+      if (relu) unpack8(ldg8(out + r * C + cv * 8), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dz = d[j];
+        if (relu && !(o[j] > 0.f)) dz = 0.f;
+        acc[0][j] += dz * (yy[j] - mu[j]) * rs[j];
+        acc[1][j] += dz;
+      }
+    }
+  }
+  block_channel_reduce<2>(acc, C8, cv, rl, RL, smem, dgamma, dbeta);
+}
+
+// BN backward pass 2: dy = gamma*rstd*(dz - dbeta/M - xhat*dgamma/M); optionally dres = dz
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, bf16* __restrict__ dy,
+                    bf16* __restrict__ dres, long M, int C, int relu) {
+  extern __shared__ float smem[];  // a[C], b[C], c[C], mean[C]:  dy = a*dz + b*y + c
+  float* ka = smem;
+  float* kb = smem + C;
+  float* kc = smem + 2 * C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma[c], rs = rstd[c], mu = mean[c];
+    const float dg = dgamma[c] * invM, db = dbeta[c] * invM;
+    // dy = g*rs*(dz - db - (y-mu)*rs*dg) = g*rs*dz - g*rs*rs*dg*y + g*rs*(mu*rs*dg - db)
+    ka[c] = g * rs;
+    kb[c] = -g * rs * rs * dg;
+    kc[c] = g * rs * (mu * rs * dg - db);
+  }
+  __syncthreads();
+  const int C8 = C / 8;
+  const long total = M * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    float d[8], yy[8], o[8];
+    unpack8(ldg8(dout + i * 8), d);
+    unpack8(ldg8(y + i * 8), yy);
+    if (relu) unpack8(ldg8(out + i * 8), o);
+    float dz[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      dz[j] = (relu && !(o[j] > 0.f)) ? 0.f : d[j];
+      d[j] = ka[cv * 8 + j] * dz[j] + kb[cv * 8 + j] * yy[j] + kc[cv * 8 + j];
+    }
+    stg8(dy + i * 8, pack8(d));
+    if (dres) stg8(dres + i * 8, pack8(dz));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Max-pool (k x k, stride, pad) NHWC, 8 channels per thread; backward recomputes the arg-max
+// (first maximum in scan order, matching PyTorch) instead of storing indices.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int P, int Q,
+                   int k, int stride, int pad) {
+  const int C8 = C / 8;
+  const long total = (long)N * P * Q * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    long t = i / C8;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int r = 0; r < k; ++r) {
+      const int h = p * stride - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int w = q * stride - pad + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ldg8(x + (((long)n * H + h) * W + w) * C + cv * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    stg8(out + i * 8, pack8(m));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ out, const bf16* __restrict__ dout,
+                   bf16* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad) {
+  // one thread per (input pixel, 8 channels): gather from every window that contains it and whose
+  // first-maximum is this pixel.
+  const int C8 = C / 8;
+  const long total = (long)N * H * W * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    long t = i / C8;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float xv[8], g[8];
+    unpack8(ldg8(x + i * 8), xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    const int p_lo = max(0, (h + pad - k + stride) / stride), p_hi = min(P - 1, (h + pad) / stride);
+    const int q_lo = max(0, (w + pad - k + stride) / stride), q_hi = min(Q - 1, (w + pad) / stride);
+    for (int p = p_lo; p <= p_hi; ++p)
+      for (int q = q_lo; q <= q_hi; ++q) {
+        float o[8], d[8];
+        const long oi = (((long)n * P + p) * Q + q) * C + cv * 8;
+        unpack8(ldg8(out + oi), o);
+        unpack8(ldg8(dout + oi), d);
+        // is (h,w) the first position in scan order attaining the max?
+        bool first[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) first[j] = (xv[j] == o[j]);
+        for (int r = 0; r < k; ++r) {
+          const int hh = p * stride - pad + r;
+          if (hh < 0 || hh >= H || hh > h) continue;
+          for (int s = 0; s < k; ++s) {
+            const int ww = q * stride - pad + s;
+            if (ww < 0 || ww >= W) continue;
+            if (hh == h && ww >= w) break;
+            float f[8];
+            unpack8(ldg8(x + (((long)n * H + hh) * W + ww) * C + cv * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (f[j] == o[j]) first[j] = false;  // an earlier element already attains the max
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (first[j]) g[j] += d[j];
+      }
+    stg8(dx + i * 8, pack8(g));
+  }
+}
+
+// Global average pool: x[N, HW, C] -> out[N, C] (bf16), and its backward (broadcast / HW)
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int HW, int C) {
+  const int C8 = C / 8;
+  const long total = (long)N * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    const int n = (int)(i / C8);
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      float f[8];
+      unpack8(ldg8(x + ((long)n * HW + p) * C + cv * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+    const float inv = 1.f / (float)HW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= inv;
+    stg8(out + i * 8, pack8(a));
+  }
+}
+__global__ void __launch_bounds__(256) gap_bwd_kernel(const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int HW, int C) {
+  const int C8 = C / 8;
+  const long total = (long)N * HW * C8;
+  const float inv = 1.f / (float)HW;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    const int n = (int)(i / ((long)HW * C8));
+    float f[8];
+    unpack8(ldg8(dout + ((long)n * C8 + cv) * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    stg8(dx + i * 8, pack8(f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused softmax cross-entropy, integer labels: one warp per row; emits per-row loss, the mean loss
+// (last-block reduction) and dlogits = (softmax - onehot) * scale in the logits dtype.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+FD_DEVINL float to_f(T v);
+template <>
+FD_DEVINL float to_f<float>(float v) { return v; }
+template <>
+FD_DEVINL float to_f<bf16>(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+FD_DEVINL T from_f(float v);
+template <>
+FD_DEVINL float from_f<float>(float v) { return v; }
+template <>
+FD_DEVINL bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_ce_kernel(const T* __restrict__ logits, const long long* __restrict__ labels, T* __restrict__ dlogits,
+                  float* __restrict__ row_loss, float* __restrict__ loss, unsigned* __restrict__ counter, int B,
+                  int Cn, long ld, float scale) {
+  const int warps = blockDim.x / 32;
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int row = blockIdx.x * warps + warp;
+  if (row < B) {
+    const T* x = logits + (long)row * ld;
+    float mx = -INFINITY;
+    for (int c = lane; c < Cn; c += 32) mx = fmaxf(mx, to_f<T>(x[c]));
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int c = lane; c < Cn; c += 32) se += __expf(to_f<T>(x[c]) - mx);
+    se = warp_sum(se);
+    const int y = (int)labels[row];
+    const float lse = __logf(se) + mx;
+    if (lane == 0) row_loss[row] = lse - to_f<T>(x[y]);
+    const float inv = 1.f / se;
+    T* d = dlogits + (long)row * ld;
+    for (int c = lane; c < Cn; c += 32) {
+      float p = __expf(to_f<T>(x[c]) - mx) * inv;
+      if (c == y) p -= 1.f;
+      d[c] = from_f<T>(p * scale);
+    }
+  }
+  // mean over rows: last block to finish sums row_loss deterministically
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    float s = 0.f;
+    for (int r = threadIdx.x; r < B; r += blockDim.x) s += row_loss[r];
+    s = warp_sum(s);
+    __shared__ float part[8];
+    if (lane == 0) part[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float tot = 0.f;
+      for (int w = 0; w < warps; ++w) tot += part[w];
+      *loss = tot / (float)B;
+      *counter = 0;
+    }
+  }
+}
+
+// uint8 NHWC [N,H,W,3] -> bf16 NHWC [N,H,W,Cpad] normalised with ImageNet mean/std; extra channels zero
+__global__ void __launch_bounds__(256)
+normalize_u8_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, long pixels, int Cpad, float m0, float m1,
+                    float m2, float s0, float s1, float s2) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < pixels; i += (long)gridDim.x * blockDim.x) {
+    const uint8_t* p = in + i * 3;
+    float f[8] = {((float)p[0] * (1.f / 255.f) - m0) * s0, ((float)p[1] * (1.f / 255.f) - m1) * s1,
+                  ((float)p[2] * (1.f / 255.f) - m2) * s2, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (Cpad == 8) {
+      stg8(out + i * 8, pack8(f));
+    } else {
+      for (int c = 0; c < Cpad; ++c) out[i * Cpad + c] = __float2bfloat16_rn(c < 3 ? f[c] : 0.f);
+    }
+  }
+}
+
+// fp32 -> bf16 cast of a flat buffer (weights arena -> compute copy)
+__global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n4) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(in)[i];
+    st_v2_u32(out + i * 4, pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// Small CUDA-core GEMM for the tiny FC-backward products (<= 0.1 GFLOP): C[M,N] (+)= op(A) op(B), fp32 out.
+// A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
+__global__ void __launch_bounds__(256)
+small_gemm_kernel(const bf16* __restrict__ A, const bf16* __restrict__ B, float* __restrict__ Cf, bf16* __restrict__ Cb,
+                  int M, int N, int K, long sam, long sak, long sbk, long sbn, long ldc) {
+  __shared__ float As[16][65];
+  __shared__ float Bs[16][65];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+      const int kk = e / 64, mm = e % 64;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < K) ? __bfloat162float(A[m * sam + k * sak]) : 0.f;
+      const int n = n0 + mm;
+      Bs[kk][mm] = (n < N && k < K) ? __bfloat162float(B[k * sbk + n * sbn]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        if (Cf) Cf[m * ldc + n] = acc[i][j];
+        if (Cb) Cb[m * ldc + n] = __float2bfloat16_rn(acc[i][j]);
+      }
+    }
+}
+
+// bias add (+ column sums for the bias gradient)
+__global__ void bias_add_kernel(bf16* __restrict__ y, const float* __restrict__ bias, int M, int N) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < (long)M * N; i += (long)gridDim.x * blockDim.x)
+    y[i] = __float2bfloat16_rn(__bfloat162float(y[i]) + bias[i % N]);
+}
+__global__ void colsum_kernel(const bf16* __restrict__ d, float* __restrict__ out, int M, int N) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int m = 0; m < M; ++m) s += __bfloat162float(d[(long)m * N + n]);
+  out[n] = s;
+}
+
+inline int grid_for(long work, int block, int cap) {
+  long g = (work + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStream_t s) {
+  if (C % 8 || C > 2048) { fd_set_error("bn_stats: C must be a multiple of 8 and <= 2048", __FILE__, __LINE__); return -1; }
+  const int C8 = C / 8;
+  if (256 % C8 && C8 < 256) { /* RL = floor; leftover threads idle */ }
+  const int RL = 256 / C8 > 0 ? 256 / C8 : 0;
+  if (RL == 0) { fd_set_error("bn_stats: C too large for this tiling", __FILE__, __LINE__); return -1; }
+  FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, C * sizeof(float), s));
+  FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, C * sizeof(float), s));
+  int grid = grid_for((M + RL - 1) / RL, 1, 148 * 8);
+  size_t sm = (size_t)RL * C * 2 * sizeof(float);
+  bn_stats_kernel<<<grid, 256, sm, s>>>(reinterpret_cast<const bf16*>(y), sum, sumsq, M, C);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, const float* sumsq, const float* gamma,
+                const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
+                float eps, float momentum, int training, int relu, cudaStream_t s) {
+  int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
+  bn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
+      reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res), reinterpret_cast<bf16*>(out), sum, sumsq,
+      gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
+              const float* gamma, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C, int relu,
+              cudaStream_t s) {
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  if (RL == 0) { fd_set_error("bn_bwd: C too large", __FILE__, __LINE__); return -1; }
+  FD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), s));
+  FD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), s));
+  int grid = grid_for((M + RL - 1) / RL, 1, 148 * 8);
+  bn_bwd_reduce_kernel<<<grid, 256, (size_t)RL * C * 2 * sizeof(float), s>>>(
+      reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
+      rstd, dgamma, dbeta, M, C, relu);
+  FD_LAUNCH_OK();
+  int grid2 = grid_for(M * C8, 256 * 4, 148 * 8);
+  bn_bwd_apply_kernel<<<grid2, 256, 3 * C * sizeof(float), s>>>(
+      reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
+      rstd, gamma, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), M, C, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s) {
+  const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
+  int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 16);
+  maxpool_fwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), N, H, W, C, P,
+                                          Q, k, stride, pad);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
+                   int stride, int pad, cudaStream_t s) {
+  const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
+  int grid = grid_for((long)N * H * W * (C / 8), 256, 148 * 16);
+  maxpool_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(out),
+                                          reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N, H, W, C,
+                                          P, Q, k, stride, pad);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s) {
+  gap_fwd_kernel<<<grid_for((long)N * (C / 8), 256, 1024), 256, 0, s>>>(reinterpret_cast<const bf16*>(x),
+                                                                       reinterpret_cast<bf16*>(out), N, HW, C);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s) {
+  gap_bwd_kernel<<<grid_for((long)N * HW * (C / 8), 256, 148 * 8), 256, 0, s>>>(reinterpret_cast<const bf16*>(dout),
+                                                                               reinterpret_cast<bf16*>(dx), N, HW, C);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_softmax_ce(const void* logits, const long long* labels, void* dlogits, float* row_loss, float* loss,
+                  unsigned* counter, int B, int Cn, long ld, float scale, int is_bf16, cudaStream_t s) {
+  const int warps = 8;
+  int grid = (B + warps - 1) / warps;
+  if (is_bf16)
+    softmax_ce_kernel<bf16><<<grid, warps * 32, 0, s>>>(reinterpret_cast<const bf16*>(logits), labels,
+                                                       reinterpret_cast<bf16*>(dlogits), row_loss, loss, counter, B,
+                                                       Cn, ld, scale);
+  else
+    softmax_ce_kernel<float><<<grid, warps * 32, 0, s>>>(reinterpret_cast<const float*>(logits), labels,
+                                                        reinterpret_cast<float*>(dlogits), row_loss, loss, counter, B,
+                                                        Cn, ld, scale);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_normalize_u8(const void* in, void* out, long pixels, int Cpad, const float* mean, const float* stdv,
+                    cudaStream_t s) {
+  normalize_u8_kernel<<<grid_for(pixels, 256, 148 * 16), 256, 0, s>>>(
+      reinterpret_cast<const uint8_t*>(in), reinterpret_cast<bf16*>(out), pixels, Cpad, mean[0], mean[1], mean[2],
+      1.f / stdv[0], 1.f / stdv[1], 1.f / stdv[2]);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_cast_f32_bf16(const float* in, void* out, long n, cudaStream_t s) {
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256, 148 * 8), 256, 0, s>>>(in, reinterpret_cast<bf16*>(out), n / 4);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_small_gemm(const void* A, const void* B, float* Cf, void* Cb, int M, int N, int K, long sam, long sak, long sbk,
+                  long sbn, long ldc, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  small_gemm_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(A), reinterpret_cast<const bf16*>(B), Cf,
+                                         reinterpret_cast<bf16*>(Cb), M, N, K, sam, sak, sbk, sbn, ldc);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_bias_add(void* y, const float* bias, int M, int N, cudaStream_t s) {
+  bias_add_kernel<<<grid_for((long)M * N, 256, 1024), 256, 0, s>>>(reinterpret_cast<bf16*>(y), bias, M, N);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_colsum(const void* d, float* out, int M, int N, cudaStream_t s) {
+  colsum_kernel<<<(N + 255) / 256, 256, 0, s>>>(reinterpret_cast<const bf16*>(d), out, M, N);
+  FD_LAUNCH_OK();
+  return 0;
+}

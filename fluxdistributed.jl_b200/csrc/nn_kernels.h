@@ -1,0 +1,25 @@
+// Host entry points of the bandwidth-bound NHWC kernels (nn_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStream_t s);
+int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, const float* sumsq, const float* gamma,
+                const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
+                float eps, float momentum, int training, int relu, cudaStream_t s);
+int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
+              const float* gamma, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C, int relu,
+              cudaStream_t s);
+int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
+int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
+                   int stride, int pad, cudaStream_t s);
+int fd_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s);
+int fd_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s);
+int fd_softmax_ce(const void* logits, const long long* labels, void* dlogits, float* row_loss, float* loss,
+                  unsigned* counter, int B, int Cn, long ld, float scale, int is_bf16, cudaStream_t s);
+int fd_normalize_u8(const void* in, void* out, long pixels, int Cpad, const float* mean, const float* stdv,
+                    cudaStream_t s);
+int fd_cast_f32_bf16(const float* in, void* out, long n, cudaStream_t s);
+int fd_small_gemm(const void* A, const void* B, float* Cf, void* Cb, int M, int N, int K, long sam, long sak, long sbk,
+                  long sbn, long ldc, cudaStream_t s);
+int fd_bias_add(void* y, const float* bias, int M, int N, cudaStream_t s);
+int fd_colsum(const void* d, float* out, int M, int N, cudaStream_t s);

@@ -95,7 +95,9 @@ class ConvBN(nn.Module):
             return conv_bn_act(x, self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
                                self.bn.running_var, residual, self.relu, self.stride, self.padding,
                                self.bn.eps, self.bn.momentum, self.training,
-                               getattr(self.conv.weight, "_lowp", None), getattr(self.conv.weight, "_gradbuf", None))
+                               getattr(self.conv.weight, "_lowp", None),
+                               (getattr(self.conv.weight, "_gradbuf", None), getattr(self.bn.weight, "_gradbuf", None),
+                                getattr(self.bn.bias, "_gradbuf", None)))
         w = self.conv.weight
         if x.dtype != w.dtype:
             w = w.to(x.dtype)

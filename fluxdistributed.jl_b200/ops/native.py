@@ -1,7 +1,18 @@
-"""Python wrappers of the sm_100a kernels (filled in alongside ``csrc/``)."""
+"""Python entry points of the sm_100a kernels (``csrc/``) and the autograd glue.
+
+Conventions: activations are logically NCHW with ``torch.channels_last`` strides
+(physically NHWC), conv weights logically ``[K,C,R,S]`` channels_last (physically
+KRSC), everything bf16 with fp32 statistics/gradients.  Each function has a plain
+PyTorch oracle in ``ops/reference.py``; ``tests/test_native_gpu.py`` compares them.
+"""
 from __future__ import annotations
 
+from typing import Optional, Tuple
+
 import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
 
 
 def _ext():
@@ -10,24 +21,275 @@ def _ext():
     return extension()
 
 
-def _todo(name):
-    def f(*a, **k):
-        raise NotImplementedError(f"native op {name} is not built yet")
+# --------------------------------------------------------------------------- layout helpers
+def nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Logical NCHW (channels_last) -> an NHWC-shaped contiguous view."""
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
 
-    f.__name__ = name
-    return f
+
+def from_nhwc(v: torch.Tensor) -> torch.Tensor:
+    """NHWC-shaped contiguous tensor -> logical NCHW channels_last view."""
+    return v.permute(0, 3, 1, 2)
 
 
-softmax_ce = _todo("softmax_ce")
-conv_fprop = _todo("conv_fprop")
-conv_dgrad = _todo("conv_dgrad")
-conv_wgrad = _todo("conv_wgrad")
-bn_stats = _todo("bn_stats")
-bn_apply = _todo("bn_apply")
-bn_bwd = _todo("bn_bwd")
-conv_bn_act = _todo("conv_bn_act")
-gap_linear = _todo("gap_linear")
-maxpool2d = _todo("maxpool2d")
-normalize_u8 = _todo("normalize_u8")
-gemm_nt = _todo("gemm_nt")
-fused_update_local = _todo("fused_update_local")
+def krsc(w: torch.Tensor) -> torch.Tensor:
+    v = w.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+# --------------------------------------------------------------------------- raw kernels
+def gemm_nt(a: torch.Tensor, b: torch.Tensor, out_dtype=BF16) -> torch.Tensor:
+    """``a[M,K] @ b[N,K]^T`` on tcgen05 (bf16 in, fp32 accumulate)."""
+    d = torch.empty(a.shape[0], b.shape[0], dtype=out_dtype, device=a.device)
+    _ext().gemm_nt(a.contiguous(), b.contiguous(), d)
+    return d
+
+
+def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
+    """``x`` NCHW/channels_last bf16, ``w`` [K,C,R,S]/channels_last bf16 -> y (same convention)."""
+    xh, wk = nhwc(x), krsc(w)
+    n, h, ww, _ = xh.shape
+    k, r, s, _ = wk.shape
+    p, q = (h + 2 * pad - r) // stride + 1, (ww + 2 * pad - s) // stride + 1
+    y = torch.empty(n, p, q, k, dtype=BF16, device=x.device)
+    _ext().conv_fprop(xh, wk, y, stride, pad)
+    return from_nhwc(y)
+
+
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int) -> torch.Tensor:
+    """Data gradient.  Stride 1 runs the tcgen05 dgrad directly; stride 2 zero-upsamples ``dy``
+    (``dy_up[2i,2j] = dy[i,j]``) and reuses the stride-1 kernel."""
+    n, c, h, ww = x_shape
+    dyh, wk = nhwc(dy), krsc(w)
+    k, r, s, _ = wk.shape
+    if stride != 1:
+        hu, wu = h + 2 * pad - r + 1, ww + 2 * pad - s + 1
+        up = torch.zeros(n, hu, wu, k, dtype=BF16, device=dy.device)
+        up[:, ::stride, ::stride][:, : dyh.shape[1], : dyh.shape[2]] = dyh
+        dyh = up
+    dx = torch.empty(n, h, ww, c, dtype=BF16, device=dy.device)
+    _ext().conv_dgrad(dyh, wk, dx, pad)
+    return from_nhwc(dx)
+
+
+def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: int,
+               out: Optional[torch.Tensor] = None, splits: int = 0) -> torch.Tensor:
+    """Weight gradient in fp32, accumulated into ``out`` (a [K,C,R,S] channels_last view of the
+    gradient arena) when given."""
+    k, c, r, s = w_shape
+    dyh, xh = nhwc(dy), nhwc(x)
+    if out is None:
+        buf = torch.zeros(k, r, s, c, dtype=torch.float32, device=dy.device)
+        _ext().conv_wgrad(dyh, xh, buf, stride, pad, splits, True)
+        return buf.permute(0, 3, 1, 2)
+    buf = out.permute(0, 2, 3, 1)
+    assert buf.is_contiguous() and buf.dtype == torch.float32
+    _ext().conv_wgrad(dyh, xh, buf, stride, pad, splits, True)
+    return out
+
+
+def bn_stats(y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Per-channel (sum, sum of squares) of an NCHW/channels_last bf16 tensor."""
+    c = y.shape[1]
+    s = torch.empty(c, dtype=torch.float32, device=y.device)
+    ss = torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_stats(nhwc(y), s, ss)
+    return s, ss
+
+
+def bn_apply(y, s, ss, gamma, beta, eps, residual=None, relu=True, running_mean=None, running_var=None,
+             momentum=0.1, training=True):
+    yh = nhwc(y)
+    out = torch.empty_like(yh)
+    c = y.shape[1]
+    mean = torch.empty(c, dtype=torch.float32, device=y.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_apply(yh, None if residual is None else nhwc(residual), out, s, ss, gamma, beta, running_mean,
+                    running_var, mean, rstd, eps, momentum, training, relu)
+    return from_nhwc(out), mean, rstd
+
+
+def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=None, dbeta=None):
+    yh = nhwc(y)
+    c = y.shape[1]
+    dy = torch.empty_like(yh)
+    dres = torch.empty_like(yh) if want_dres else None
+    dgamma = dgamma if dgamma is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    dbeta = dbeta if dbeta is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_bwd(nhwc(dout), yh, nhwc(out) if relu else None, mean, rstd, gamma, dgamma, dbeta, dy, dres, relu)
+    return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
+
+
+def normalize_u8(x_u8: torch.Tensor, cpad: int = 3, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """uint8 NHWC [N,H,W,3] -> bf16 logical NCHW (channels_last) with ``cpad`` channels."""
+    n, h, w, _ = x_u8.shape
+    out = torch.empty(n, h, w, cpad, dtype=BF16, device=x_u8.device)
+    _ext().normalize_u8(x_u8.contiguous(), out, list(mean), list(std))
+    return from_nhwc(out)
+
+
+# --------------------------------------------------------------------------- autograd: loss
+class _SoftmaxCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        lg = logits if logits.stride(-1) == 1 else logits.contiguous()
+        b = lg.shape[0]
+        dl = torch.empty_like(lg)
+        row = torch.empty(b, dtype=torch.float32, device=lg.device)
+        loss = torch.empty((), dtype=torch.float32, device=lg.device)
+        ctr = torch.zeros(1, dtype=torch.int32, device=lg.device)
+        _ext().softmax_ce(lg, labels.long(), dl, row, loss, ctr, 1.0 / b)
+        ctx.save_for_backward(dl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return dl * g.to(dl.dtype), None
+
+
+def softmax_ce(logits: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    """Mean softmax cross-entropy with integer labels: loss and dlogits from one kernel (K9)."""
+    from . import native_available
+
+    if not (logits.is_cuda and native_available() and logits.dtype in (BF16, torch.float32)):
+        return F.cross_entropy(logits.float(), labels.long())
+    return _SoftmaxCE.apply(logits, labels)
+
+
+# --------------------------------------------------------------------------- autograd: conv + BN + act
+def _tc_ok(cin: int, cout: int) -> bool:
+    return cin % 64 == 0 and cout % 64 == 0
+
+
+class _ConvBNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
+                w_gradbuf):
+        wl = w_lowp if w_lowp is not None else w.detach().to(BF16)
+        if not wl.permute(0, 2, 3, 1).is_contiguous():
+            wl = wl.contiguous(memory_format=torch.channels_last)
+        x = x if x.dtype == BF16 else x.to(BF16)
+        tc = _tc_ok(w.shape[1], w.shape[0])
+        if tc:
+            y = conv_fprop(x, wl, stride, pad)
+        else:  # C=3 stem: tensor-core tiling needs C%64==0 (space-to-depth stem is the planned native path)
+            y = F.conv2d(x, wl, None, stride, pad)
+            y = y.contiguous(memory_format=torch.channels_last)
+        if training:
+            s, ss = bn_stats(y)
+        else:
+            s = ss = gamma  # unused
+        out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
+        ctx.save_for_backward(x, wl, y, out if relu else None, mean, rstd, gamma)
+        ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape))
+        ctx.w_gradbuf, ctx.g_gradbuf, ctx.b_gradbuf = w_gradbuf if isinstance(w_gradbuf, tuple) else (w_gradbuf, None, None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, wl, y, out, mean, rstd, gamma = ctx.saved_tensors
+        relu, stride, pad, has_res, tc, w_shape, x_shape = ctx.cfg
+        dout = dout if dout.dtype == BF16 else dout.to(BF16)
+        dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
+                                         dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
+        if ctx.g_gradbuf is not None:  # landed in the arena: autograd must not accumulate them again
+            dgamma = dbeta = None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            if tc:
+                dx = conv_dgrad(dy, wl, x_shape, stride, pad)
+            else:
+                dx = torch.nn.grad.conv2d_input(x_shape, wl, dy, stride, pad)
+        if tc:
+            gw = conv_wgrad(dy, x, w_shape, stride, pad, out=ctx.w_gradbuf)
+        else:
+            gw = torch.nn.grad.conv2d_weight(x.float(), w_shape, dy.float(), stride, pad)
+            if ctx.w_gradbuf is not None:
+                ctx.w_gradbuf.add_(gw)
+                gw = ctx.w_gradbuf
+        # when the gradient already landed in the arena, autograd must not add it a second time
+        dw = None if ctx.w_gradbuf is not None else gw
+        return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
+                None, None)
+
+
+def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
+                w_gradbuf=None):
+    return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
+                            w_gradbuf)
+
+
+# --------------------------------------------------------------------------- autograd: max-pool, GAP + FC
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        xh = nhwc(x)
+        n, h, w, c = xh.shape
+        p, q = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+        out = torch.empty(n, p, q, c, dtype=x.dtype, device=x.device)
+        _ext().maxpool_fwd(xh, out, k, stride, pad)
+        ctx.save_for_backward(xh, out)
+        ctx.cfg = (k, stride, pad)
+        return from_nhwc(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xh, out = ctx.saved_tensors
+        dx = torch.empty_like(xh)
+        _ext().maxpool_bwd(xh, out, nhwc(dout.to(xh.dtype)), dx, *ctx.cfg)
+        return from_nhwc(dx), None, None, None
+
+
+def maxpool2d(x, k=3, stride=2, pad=1):
+    return _MaxPool.apply(x, k, stride, pad)
+
+
+class _GapLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, w_lowp, w_gradbuf, b_gradbuf):
+        xh = nhwc(x)
+        n, h, ww, c = xh.shape
+        pooled = torch.empty(n, c, dtype=BF16, device=x.device)
+        _ext().gap_fwd(xh, pooled)
+        wl = w_lowp if w_lowp is not None else w.detach().to(BF16)
+        logits = gemm_nt(pooled, wl)                       # tcgen05, [n, classes]
+        if b is not None:
+            _ext().bias_add(logits, b.detach().float())
+        ctx.save_for_backward(pooled, wl)
+        ctx.cfg = (tuple(xh.shape), b is not None)
+        ctx.bufs = (w_gradbuf, b_gradbuf)
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        pooled, wl = ctx.saved_tensors
+        (n, h, ww, c), has_b = ctx.cfg
+        w_gradbuf, b_gradbuf = ctx.bufs
+        d = dlogits.contiguous().to(BF16)
+        ncls = d.shape[1]
+        e = _ext()
+        # dW[cls, c] = sum_n d[n, cls] * pooled[n, c]
+        gw = w_gradbuf if w_gradbuf is not None else torch.empty(ncls, c, dtype=torch.float32, device=d.device)
+        e.small_gemm(d, pooled, gw, ncls, c, n, 1, ncls, c, 1)
+        gb = None
+        if has_b:
+            gb = b_gradbuf if b_gradbuf is not None else torch.empty(ncls, dtype=torch.float32, device=d.device)
+            e.colsum(d, gb)
+        # dpooled[n, c] = sum_cls d[n, cls] * W[cls, c]
+        dp = torch.empty(n, c, dtype=BF16, device=d.device)
+        e.small_gemm(d, wl, dp, n, c, ncls, ncls, 1, c, 1)
+        dx = torch.empty(n, h, ww, c, dtype=BF16, device=d.device)
+        e.gap_bwd(dp, dx)
+        return (from_nhwc(dx), None if w_gradbuf is not None else gw,
+                (None if (b_gradbuf is not None or not has_b) else gb), None, None, None)
+
+
+def gap_linear(x, w, b, w_lowp=None):
+    return _GapLinear.apply(x, w, b, w_lowp, getattr(w, "_gradbuf", None),
+                            getattr(b, "_gradbuf", None) if b is not None else None)
+
+
+def fused_update_local(*a, **k):  # kept for API symmetry; the engine builds FusedPlan objects directly
+    raise NotImplementedError("use parallel.native_comm.NativeComm")

@@ -54,8 +54,11 @@ class FlatArena:
     """Flat, identically laid out buffers for one replica."""
 
     def __init__(self, model: nn.Module, device: torch.device, n_slots: int, lowp: Optional[torch.dtype],
-                 world: int, alloc: Optional[Callable[[int, torch.dtype], torch.Tensor]] = None):
+                 world: int, alloc: Optional[Callable[[int, torch.dtype], torch.Tensor]] = None,
+                 sort_lowp_first: bool = False):
         self.params = [p for p in model.parameters() if p.requires_grad]
+        if sort_lowp_first:  # matrices/filters first, 1-D (BN affine, biases) last: see native_comm
+            self.params = sorted(self.params, key=lambda p: p.dim() < 2)
         self.offsets: List[int] = []
         off = 0
         for p in self.params:
@@ -81,14 +84,15 @@ class FlatArena:
 
 class FusedReplica:
     def __init__(self, model: nn.Module, dev, opt: Rule, world: int, rank: int, lowp: Optional[torch.dtype],
-                 alloc=None):
+                 alloc=None, sort_lowp_first: bool = False):
         self.model, self.dev, self.opt = model, as_device(dev), opt
         self.world, self.rank = world, rank
         self.step_count = 0
         self.group: Optional["FusedGroup"] = None
+        self.stream = None  # set by the group when several replicas share one GPU (virtual replicas)
         tdev = self.dev.torch_device
         with device_ctx(self.dev):
-            self.arena = FlatArena(model, tdev, opt.n_slots, lowp, world, alloc)
+            self.arena = FlatArena(model, tdev, opt.n_slots, lowp, world, alloc, sort_lowp_first)
             a = self.arena
             with torch.no_grad():
                 for i, p in enumerate(a.params):
@@ -130,6 +134,13 @@ class FusedReplica:
         self.arena.g32.zero_()
 
     def step(self, x, y, loss: Callable, fused_update: bool = True):
+        if self.stream is not None:
+            with device_ctx(self.dev), torch.cuda.stream(self.stream):
+                self.stream.wait_stream(torch.cuda.default_stream(self.dev.torch_device))
+                l = self.forward_backward(x, y, loss)
+                if fused_update:
+                    self.reduce_and_update()
+                return l
         l = self.forward_backward(x, y, loss)
         if fused_update:
             self.reduce_and_update()
@@ -161,9 +172,10 @@ class FusedReplica:
         flat = [v for _, v in leaves(st)] if st is not None else []
         self.step_count = step_count
         # walk model params in order and copy moments in
-        it = iter(self._state_leaves(st))
-        for i, _p in enumerate(a.params):
-            s = next(it, None)
+        idx = {id(p): i for i, p in enumerate(a.params)}
+        model_params = [p for p in self.model.parameters() if p.requires_grad]
+        for p, s in zip(model_params, self._state_leaves(st)):
+            i = idx[id(p)]
             if s is None:
                 continue
             if isinstance(s, tuple):
@@ -250,6 +262,13 @@ class FusedGroup:
         self.loss = loss
         for r in self.replicas:
             r.group = self
+        # replicas that share a physical GPU must run on distinct streams, otherwise the device-side
+        # barrier of the fused kernel would wait for a kernel queued behind it on the same stream
+        cu = [r.dev.cuda_index for r in self.replicas if r.dev.is_cuda]
+        if len(cu) != len(set(cu)):
+            for r in self.replicas:
+                with device_ctx(r.dev):
+                    r.stream = torch.cuda.Stream(device=r.dev.torch_device)
 
     # ---- constructors
     @staticmethod
@@ -306,6 +325,8 @@ class FusedGroup:
     def set_opt(self, opt: Rule) -> None:
         for r in self.replicas:
             r.opt = opt
+            if hasattr(self.comm, "set_opt"):
+                self.comm.set_opt(r, opt)
 
     def sync_to_modules(self) -> None:
         """Make every module's fp32 parameters current (gathers owner shards when
