@@ -14,6 +14,8 @@
 
 const char* fd_last_error();
 long fd_launch_count();
+int fd_probe_shift(const void* A, const void* B, float* D, int rows, int shift, int sbo, int base_off, int mn_major,
+                   int nk16, cudaStream_t s);
 
 namespace {
 
@@ -247,6 +249,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_bwd", &bn_bwd);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("upsample_zero", [](at::Tensor dy, at::Tensor up, int stride) {
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_upsample_zero(dy.data_ptr(), up.data_ptr(), (int)dy.size(0), (int)dy.size(1), (int)dy.size(2), (int)up.size(1),
+                           (int)up.size(2), (int)dy.size(3), stride, cur_stream()), "upsample_zero");
+  });
   m.def("gap_fwd", &gap_fwd);
   m.def("gap_bwd", &gap_bwd);
   m.def("softmax_ce", &softmax_ce);
@@ -256,6 +263,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_add", &bias_add);
   m.def("colsum", &colsum);
   m.def("enable_peer_access", &enable_peer_access);
+  m.def("probe_shift", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, int base_off, bool mn_major, int nk16) {
+    c10::cuda::CUDAGuard guard(A.device());
+    check(fd_probe_shift(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, base_off, mn_major, nk16,
+                         cur_stream()), "probe_shift");
+  });
   m.def("num_sms", &fd_num_sms);
   m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
   fd_bind_staging(m);

@@ -268,16 +268,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int col0 = nt * BN + c0;
             if (P.out_fp32) {
               float* o = reinterpret_cast<float*>(P.out) + (long)row * P.ldo + col0;
+              const bool vec = (P.ldo & 3) == 0;
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (col0 + j + 4 <= P.N)
+              for (int j = 0; j < 32; j += 4) {
+                if (vec && col0 + j + 4 <= P.N) {
                   *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                   __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                } else {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e)
+                    if (col0 + j + e < P.N) o[j + e] = __uint_as_float(v[j + e]);
+                }
+              }
             } else {
               bf16* o = reinterpret_cast<bf16*>(P.out) + (long)row * P.ldo + col0;
+              const bool vec = (P.ldo & 7) == 0;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                if (col0 + j + 8 <= P.N) {
+                if (!(vec && col0 + j + 8 <= P.N)) {  // ragged / unaligned rows (e.g. 100-class head)
+#pragma unroll
+                  for (int e = 0; e < 8; ++e)
+                    if (col0 + j + e < P.N) o[j + e] = __float2bfloat16_rn(__uint_as_float(v[j + e]));
+                } else {
                   uint4 u;
                   u.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
                   u.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));

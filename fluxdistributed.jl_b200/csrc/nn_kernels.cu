@@ -237,54 +237,77 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, in
 }
 
 __global__ void __launch_bounds__(256)
-maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ out, const bf16* __restrict__ dout,
-                   bf16* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad) {
-  // one thread per (input pixel, 8 channels): gather from every window that contains it and whose
-  // first-maximum is this pixel.
+maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int H,
+                   int W, int C, int P, int Q, int k, int stride, int pad) {
+  // one thread per (output window, 8 channels): recompute the arg-max (first maximum in scan order, like
+  // PyTorch) and scatter the window's gradient there with native bf16x2 atomics; dx is pre-zeroed.
   const int C8 = C / 8;
-  const long total = (long)N * H * W * C8;
+  const long total = (long)N * P * Q * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int cv = (int)(i % C8);
     long t = i / C8;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    float xv[8], g[8];
-    unpack8(ldg8(x + i * 8), xv);
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    float m[8];
+    int am[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = 0.f;
-    const int p_lo = max(0, (h + pad - k + stride) / stride), p_hi = min(P - 1, (h + pad) / stride);
-    const int q_lo = max(0, (w + pad - k + stride) / stride), q_hi = min(Q - 1, (w + pad) / stride);
-    for (int p = p_lo; p <= p_hi; ++p)
-      for (int q = q_lo; q <= q_hi; ++q) {
-        float o[8], d[8];
-        const long oi = (((long)n * P + p) * Q + q) * C + cv * 8;
-        unpack8(ldg8(out + oi), o);
-        unpack8(ldg8(dout + oi), d);
-        // is (h,w) the first position in scan order attaining the max?
-        bool first[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) first[j] = (xv[j] == o[j]);
-        for (int r = 0; r < k; ++r) {
-          const int hh = p * stride - pad + r;
-          if (hh < 0 || hh >= H || hh > h) continue;
-          for (int s = 0; s < k; ++s) {
-            const int ww = q * stride - pad + s;
-            if (ww < 0 || ww >= W) continue;
-            if (hh == h && ww >= w) break;
-            float f[8];
-            unpack8(ldg8(x + (((long)n * H + hh) * W + ww) * C + cv * 8), f);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (f[j] == o[j]) first[j] = false;  // an earlier element already attains the max
-          }
-        }
+    for (int j = 0; j < 8; ++j) {
+      m[j] = -INFINITY;
+      am[j] = -1;
+    }
+    for (int r = 0; r < k; ++r) {
+      const int h = p * stride - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int w = q * stride - pad + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        unpack8(ldg8(x + (((long)n * H + h) * W + w) * C + cv * 8), f);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          if (first[j]) g[j] += d[j];
+          if (f[j] > m[j]) {
+            m[j] = f[j];
+            am[j] = h * W + w;
+          }
       }
-    stg8(dx + i * 8, pack8(g));
+    }
+    float d[8];
+    unpack8(ldg8(dout + i * 8), d);
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      bf16* base = dx + (long)n * H * W * C + cv * 8 + j;
+      if (am[j] == am[j + 1]) {
+        if (am[j] >= 0)
+          atomicAdd(reinterpret_cast<bf162*>(base + (long)am[j] * C), __floats2bfloat162_rn(d[j], d[j + 1]));
+      } else {
+        if (am[j] >= 0) atomicAdd(reinterpret_cast<bf162*>(base + (long)am[j] * C), __floats2bfloat162_rn(d[j], 0.f));
+        if (am[j + 1] >= 0)
+          atomicAdd(reinterpret_cast<bf162*>(base + (long)am[j + 1] * C), __floats2bfloat162_rn(0.f, d[j + 1]));
+      }
+    }
+  }
+}
+
+// zero-insertion upsample for strided dgrad: up[n, st*p, st*q, :] = dy[n,p,q,:], zeros elsewhere (one pass)
+__global__ void __launch_bounds__(256)
+upsample_zero_kernel(const bf16* __restrict__ dy, bf16* __restrict__ up, int N, int P, int Q, int HU, int WU, int C,
+                     int stride) {
+  const int C8 = C / 8;
+  const long total = (long)N * HU * WU * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    long t = i / C8;
+    const int w = (int)(t % WU);
+    t /= WU;
+    const int h = (int)(t % HU);
+    const int n = (int)(t / HU);
+    V8 v;
+    v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
+    if (h % stride == 0 && w % stride == 0 && h / stride < P && w / stride < Q)
+      v = ldg8(dy + ((((long)n * P + h / stride) * Q + w / stride) * C8 + cv) * 8);
+    stg8(up + i * 8, v);
   }
 }
 
@@ -547,11 +570,19 @@ int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, 
 }
 int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
                    int stride, int pad, cudaStream_t s) {
+  (void)out;
   const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
-  int grid = grid_for((long)N * H * W * (C / 8), 256, 148 * 16);
-  maxpool_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(out),
-                                          reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N, H, W, C,
-                                          P, Q, k, stride, pad);
+  FD_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)N * H * W * C * 2, s));
+  int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 16);
+  maxpool_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dout),
+                                          reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q, k, stride, pad);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_upsample_zero(const void* dy, void* up, int N, int P, int Q, int HU, int WU, int C, int stride, cudaStream_t s) {
+  int grid = grid_for((long)N * HU * WU * (C / 8), 256, 148 * 16);
+  upsample_zero_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<bf16*>(up), N, P, Q, HU,
+                                            WU, C, stride);
   FD_LAUNCH_OK();
   return 0;
 }

@@ -12,6 +12,7 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
 int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
 int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
                    int stride, int pad, cudaStream_t s);
+int fd_upsample_zero(const void* dy, void* up, int N, int P, int Q, int HU, int WU, int C, int stride, cudaStream_t s);
 int fd_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s);
 int fd_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s);
 int fd_softmax_ce(const void* logits, const long long* labels, void* dlogits, float* row_loss, float* loss,

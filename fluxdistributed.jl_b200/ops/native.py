@@ -65,8 +65,8 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int
     k, r, s, _ = wk.shape
     if stride != 1:
         hu, wu = h + 2 * pad - r + 1, ww + 2 * pad - s + 1
-        up = torch.zeros(n, hu, wu, k, dtype=BF16, device=dy.device)
-        up[:, ::stride, ::stride][:, : dyh.shape[1], : dyh.shape[2]] = dyh
+        up = torch.empty(n, hu, wu, k, dtype=BF16, device=dy.device)
+        _ext().upsample_zero(dyh, up, stride)
         dyh = up
     dx = torch.empty(n, h, ww, c, dtype=BF16, device=dy.device)
     _ext().conv_dgrad(dyh, wk, dx, pad)

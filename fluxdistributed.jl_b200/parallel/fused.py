@@ -301,11 +301,16 @@ class FusedGroup:
         default (or given) ``torch.distributed`` group."""
         import torch.distributed as dist
 
+        import os
+
         dev = as_device(dev)
-        if not dist.is_initialized():
+        if not dist.is_initialized() and int(os.environ.get("WORLD_SIZE", "1")) > 1:
             backend = "nccl" if dev.is_cuda else "gloo"
             dist.init_process_group(backend, device_id=dev.torch_device if dev.is_cuda else None)
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if dist.is_initialized():
+            world, rank = dist.get_world_size(group), dist.get_rank(group)
+        else:  # a single stand-alone process: world of one, no process group needed
+            world, rank = 1, 0
         lowp = cls._lowp(dtype, [dev])
         use_native = comm == "native" or (comm == "auto" and dev.is_cuda and _native_ok())
         if use_native:
@@ -319,7 +324,8 @@ class FusedGroup:
             dist.broadcast(rep.arena.w32, src=0, group=group)
             if rep.arena.w16 is not None:
                 rep.arena.w16.copy_(rep.arena.w32)
-        return cls([rep], DistComm(group), loss)
+            return cls([rep], DistComm(group), loss)
+        return cls([rep], ThreadComm([rep]), loss)
 
     # ---- API used by task.train / process workers
     def set_opt(self, opt: Rule) -> None:

@@ -53,7 +53,7 @@ def _lowp_only_boundary(model: nn.Module, arena: FlatArena) -> int:
         return 0
     lowp_ids = set()
     for m in model.modules():
-        if isinstance(m, ConvBN) and m.cin % 64 == 0 and m.cout % 64 == 0:
+        if isinstance(m, ConvBN):  # every ConvBN reads its filter through the bf16 copy (tcgen05 or stem path)
             lowp_ids.add(id(m.conv.weight))
         elif isinstance(m, Head):
             lowp_ids.add(id(m.fc.weight))
@@ -134,10 +134,6 @@ class NativeComm:
             import torch.distributed._symmetric_memory as symm
 
             gname = (group or dist.group.WORLD).group_name
-            try:
-                symm.enable_symm_mem_for_group(gname)
-            except Exception:
-                pass
 
             def alloc(nel, dt):
                 t = symm.empty(nel, dtype=dt, device=tdev)

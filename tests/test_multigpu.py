@@ -1,0 +1,125 @@
+"""Multi-GPU correctness of the fused all-reduce+update kernel: task mode (threads, UVA peer
+pointers) and process mode (torch symmetric memory; P2P and NVLS multicast variants).
+After one synchronised step all replicas must be bit-identical and match the single-device
+full-batch step."""
+import copy
+import os
+import socket
+from concurrent.futures import ThreadPoolExecutor
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import fluxdist as fd
+from fluxdist.tree import gradient
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu, pytest.mark.timeout(300)]
+
+
+def _batches(n, per=4):
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(n * per, 3, 32, 32, generator=g)
+    y = fd.onehot(torch.randint(0, 10, (n * per,), generator=g), 10)
+    return x, y
+
+
+def _reference(base, opt, x, y, steps):
+    ref, st = copy.deepcopy(base), fd.state(opt, base)
+    for _ in range(steps):
+        g, _ = gradient(lambda m: fd.logitcrossentropy(m(x), y), ref)
+        ref, st = opt(ref, g, st)
+    return ref, st
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("opt", [fd.Momentum(0.01, 0.9), fd.ADAM()])
+def test_thread_mode_real_gpus(mode, opt):
+    from fluxdist.parallel import FusedGroup
+
+    n = min(torch.cuda.device_count(), 4)
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    devs = fd.cuda_devices(n)
+    grp = FusedGroup.for_threads([copy.deepcopy(base).to(d.torch_device) for d in devs], devs, opt,
+                                 dtype=torch.float32, comm="native", mode=mode)
+    for r in grp.replicas:
+        grp.comm.plans[id(r)][0].set_max_spins(1 << 23)
+    x, y = _batches(n)
+    per = x.shape[0] // n
+    with ThreadPoolExecutor(n) as ex:
+        for _ in range(3):
+            futs = [ex.submit(grp.replicas[i].step, x[per * i:per * (i + 1)].to(devs[i].torch_device),
+                              y[per * i:per * (i + 1)].to(devs[i].torch_device), fd.logitcrossentropy) for i in range(n)]
+            [f.result() for f in futs]
+    for d in devs:
+        torch.cuda.synchronize(d.torch_device)
+    assert all(grp.comm.status(r) == (False, False) for r in grp.replicas)
+    grp.sync_to_modules()
+    ref, st = _reference(base, opt, x, y, 3)
+    for r in grp.replicas:
+        for a, b in zip(r.model.parameters(), ref.parameters()):
+            assert torch.allclose(a.detach().cpu(), b, rtol=1e-3, atol=2e-4)
+    for a, b in zip(grp.replicas[0].model.parameters(), grp.replicas[-1].model.parameters()):
+        assert torch.equal(a.detach().cpu(), b.detach().cpu())
+    assert fd.compare(fd.to_cpu(grp.state_trees()[devs[0]]), st, 1e-3, 1e-4)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _proc(rank, world, port, nvls, mode, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank), FLUXDIST_NVLS="1" if nvls else "0")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from fluxdist.parallel import FusedGroup
+
+    torch.manual_seed(rank + 10)  # rank-specific init: the group must broadcast rank 0's weights
+    m = fd.tiny_convnet(10).cuda()
+    opt = fd.Momentum(0.01, 0.9)
+    grp = FusedGroup.for_process(m, fd.CudaDevice(rank, rank), opt, dtype=torch.float32, comm="native", mode=mode)
+    rep = grp.replicas[0]
+    grp.comm.plans[id(rep)][0].set_max_spins(1 << 23)
+    x, y = _batches(world)
+    per = x.shape[0] // world
+    for _ in range(3):
+        rep.step(x[per * rank:per * (rank + 1)].cuda(), y[per * rank:per * (rank + 1)].cuda(), fd.logitcrossentropy)
+    torch.cuda.synchronize()
+    st = grp.comm.status(rep)
+    grp.sync_to_modules()
+    q.put((rank, [p.detach().cpu().clone() for p in m.parameters()], st, rep.comm_info))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("nvls,mode", [(False, 0), (True, 0), (False, 1)])
+def test_process_mode_symmetric_memory(nvls, mode):
+    world = min(torch.cuda.device_count(), 4)
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_proc, args=(r, world, port, nvls, mode, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = {}
+    for _ in range(world):
+        r = q.get(timeout=240)
+        res[r[0]] = r
+    [p.join(60) for p in ps]
+    torch.manual_seed(10)
+    base = fd.tiny_convnet(10)
+    x, y = _batches(world)
+    ref, _ = _reference(base, fd.Momentum(0.01, 0.9), x, y, 3)
+    print("comm_info", res[0][3])
+    for r in range(world):
+        assert res[r][2] == (False, False)
+        for a, b, c in zip(res[r][1], res[0][1], ref.parameters()):
+            assert torch.equal(a, b)
+            assert torch.allclose(a, c, rtol=1e-3, atol=2e-4)
