@@ -14,6 +14,8 @@
 
 const char* fd_last_error();
 long fd_launch_count();
+int fd_probe_shift32(const void* A, const void* B, float* D, int rows, int shift, int sbo, int mn_major, cudaStream_t s);
+int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, cudaStream_t s);
 int fd_probe_shift(const void* A, const void* B, float* D, int rows, int shift, int sbo, int base_off, int mn_major,
                    int nk16, cudaStream_t s);
 
@@ -244,6 +246,22 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_fprop", &conv_fprop);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);
+  m.def("conv3x3_fprop", [](at::Tensor x, at::Tensor w, at::Tensor y, c10::optional<at::Tensor> sum,
+                            c10::optional<at::Tensor> sumsq, int variant) {
+    c10::cuda::CUDAGuard guard(x.device());
+    check(fd_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x.size(0), (int)x.size(1),
+                           (int)x.size(2), (int)x.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_fprop");
+  });
+  m.def("conv3x3_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int variant) {
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_conv3x3_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+                           (int)dx.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_dgrad");
+  });
+  m.def("conv3x3_wgrad", [](at::Tensor dy, at::Tensor x, at::Tensor dw, int splits) {
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                           (int)x.size(3), (int)dy.size(3), splits, cur_stream()), "conv3x3_wgrad");
+  });
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd", &bn_bwd);
@@ -263,6 +281,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_add", &bias_add);
   m.def("colsum", &colsum);
   m.def("enable_peer_access", &enable_peer_access);
+  m.def("probe_shift32", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, bool mn_major) {
+    c10::cuda::CUDAGuard guard(A.device());
+    check(fd_probe_shift32(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, mn_major, cur_stream()),
+          "probe_shift32");
+  });
+  m.def("probe_mma_rate", [](at::Tensor out, int bn, int reps, int shift, int sbo) {
+    c10::cuda::CUDAGuard guard(out.device());
+    check(fd_probe_mma_rate(reinterpret_cast<long long*>(out.data_ptr<int64_t>()), bn, reps, shift, sbo, cur_stream()), "probe_mma_rate");
+  });
   m.def("probe_shift", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, int base_off, bool mn_major, int nk16) {
     c10::cuda::CUDAGuard guard(A.device());
     check(fd_probe_shift(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, base_off, mn_major, nk16,

@@ -1,0 +1,637 @@
+// Halo-tile 3x3 / stride-1 convolution on tcgen05 (fprop and dgrad) — the hot convs of ResNet-18/34.
+//
+// The im2col kernels (igemm_sm100.cu) re-read the activation tile once per filter tap (9x L2 traffic) and are
+// L2-bandwidth-bound on B200 (profiles/r1_launches_native_v0.csv).  Here a CTA owns a 16x8 output-pixel tile:
+//   * ONE tiled-mode TMA load per 64-channel chunk brings the (16+2)x(8+2) input patch into shared memory
+//     (180 pixel rows of 128 B, 128B-swizzled; out-of-image halo rows/cols are zero-filled by the copy engine);
+//   * every filter tap (r,s) is the SAME patch seen through a UMMA descriptor whose start address is shifted by
+//     (r*10+s) rows and whose 8-row-group stride (SBO) is the patch pitch (1280 B) — legal because the swizzle
+//     XOR is a function of the absolute shared-memory address (profiles/umma_shifted_descriptor_probe.txt);
+//   * the filter slice of the CTA's output-channel tile is either RESIDENT in shared memory for the whole
+//     persistent kernel (stages 1-2: 72-144 KB) or streamed through its own TMA ring;
+//   * accumulators are double-buffered in TMEM; the epilogue converts to bf16, stores NHWC rows and (fprop)
+//     accumulates the BatchNorm batch statistics (per-channel sum / sum of squares) with a warp
+//     transpose-reduce + one atomicAdd per channel, so no separate statistics pass reads y again (K4 fused).
+// dgrad is the same kernel with flipped taps and the filter read N-major (W[k,r,s,c] rows = k).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "igemm.h"
+
+namespace {
+
+constexpr int TH = 16, TW = 8;       // output tile (pixels); TW = 8 = one swizzle-atom row group
+constexpr int PH = TH + 2, PW = TW + 2;
+constexpr int PATCH_BYTES = PH * PW * 128;                       // 23040
+constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;  // 23552
+constexpr int kThreads = 192;
+
+struct HParams {
+  int N, H, W;          // image batch / output extent (stride 1, same size)
+  int Cred;             // reduction channels (C for fprop, K for dgrad)
+  int Nout;             // output channels (K for fprop, C for dgrad)
+  int chunks;           // Cred / 64
+  int tiles_h, tiles_w, m_tiles, n_tiles;
+  int wcols;            // weight-matrix tap stride in elements (= C of the filter tensor)
+  void* out;
+  float* sum;
+  float* sumsq;
+  int dbg;  // debug/ablation bits: 1 = skip output stores, 2 = skip patch loads, 4 = skip MMAs
+};
+
+template <int BN, bool DGRAD, bool RESIDENT>
+struct HCfg {
+  static constexpr int B_TILE = BN * 128;  // one (tap, chunk) filter tile: BN x 64 bf16
+  static constexpr int A_STAGES = RESIDENT ? 2 : 3;
+  static constexpr int B_STAGES = RESIDENT ? 0 : 6;
+  static constexpr int TMEM_COLS = 2 * BN;
+};
+
+FD_DEVINL float2 colsum_transpose_reduce(float (&v)[32], int lane) {
+  // v[c] = this lane's value for column c; returns (sum over lanes of column `lane`, unused)
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const bool up = (lane & off) != 0;
+      const float keep = up ? v[j + off] : v[j];
+      const float send = up ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return make_float2(v[0], 0.f);
+}
+
+template <int BN, bool DGRAD, bool RESIDENT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HParams P,
+                 const int resident_bytes, const int a_stages) {
+  using C = HCfg<BN, DGRAD, RESIDENT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + a_stages * PATCH_STRIDE;
+  const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemB + b_bytes);
+  uint64_t* a_full = bars;                 // [a_stages <= 8]
+  uint64_t* a_empty = bars + 8;            // [a_stages]
+  uint64_t* b_full = bars + 16;            // [B_STAGES] (streamed) or [1] (resident)
+  uint64_t* b_empty = bars + 24;           // [B_STAGES]
+  uint64_t* tfull = bars + 32;
+  uint64_t* tempty = bars + 34;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1);
+      mbar_init(&a_empty[i], 1);
+    }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&b_full[i], 1);
+      mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // each CTA serves one output-channel tile (so a resident filter slice stays valid) and strides over m-tiles
+  const int nt = blockIdx.x % P.n_tiles;
+  const int n0 = nt * BN;
+  const int m_first = blockIdx.x / P.n_tiles;
+  const int m_step = gridDim.x / P.n_tiles;
+  const int taps = 9;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      if (RESIDENT) {
+        mbar_arrive_expect_tx(&b_full[0], resident_bytes);
+        for (int ch = 0; ch < P.chunks; ++ch)
+          for (int tp = 0; tp < taps; ++tp) {
+            uint8_t* dst = smemB + (ch * taps + tp) * C::B_TILE;
+            if (!DGRAD) {
+              tma_load_2d(dst, &mapB, &b_full[0], tp * P.wcols + ch * 64, n0);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(dst + j * 8192, &mapB, &b_full[0], tp * P.wcols + n0 + j * 64, ch * 64);
+            }
+          }
+      }
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
+        const int n = mt / (P.tiles_h * P.tiles_w);
+        const int rem = mt - n * (P.tiles_h * P.tiles_w);
+        const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+        const int h0 = th * TH, w0 = tw * TW;
+        for (int ch = 0; ch < P.chunks; ++ch) {
+          mbar_wait(&a_empty[as], aph ^ 1);
+          if (P.dbg & 2) {
+            mbar_arrive(&a_full[as]);
+          } else {
+            mbar_arrive_expect_tx(&a_full[as], PATCH_BYTES);
+            tma_load_4d(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], ch * 64, w0 - 1, h0 - 1, n);
+          }
+          if (++as == a_stages) {
+            as = 0;
+            aph ^= 1;
+          }
+          if (!RESIDENT) {
+            for (int tp = 0; tp < taps; ++tp) {
+              mbar_wait(&b_empty[bs], bph ^ 1);
+              mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
+              uint8_t* dst = smemB + bs * C::B_TILE;
+              if (!DGRAD) {
+                tma_load_2d(dst, &mapB, &b_full[bs], tp * P.wcols + ch * 64, n0);
+              } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                  tma_load_2d(dst + j * 8192, &mapB, &b_full[bs], tp * P.wcols + n0 + j * 64, ch * 64);
+              }
+              if (++bs == (RESIDENT ? 1 : C::B_STAGES)) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // Issue loop.  One thread feeds the tensor core, so the loop must cost a few instructions per MMA: the two
+    // shared-memory descriptors are a precomputed 64-bit base plus a 14-bit address field, and the tap / k offsets
+    // are compile-time immediates of the fully unrolled 9 x 4 loop.
+    constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, DGRAD ? 1 : 0);
+    const uint64_t descA0 = umma_smem_desc(0, 16, PW * 128, UMMA_LAYOUT_SW128);
+    const uint64_t descB0 = DGRAD ? umma_smem_desc(0, 8192, 1024, UMMA_LAYOUT_SW128)
+                                  : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+    int as = 0, bs = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, accph = 0;
+    if (RESIDENT) {
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+    }
+    const uint32_t smemA16 = smem_u32(smemA) >> 4, smemB16 = smem_u32(smemB) >> 4;
+    for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
+      mbar_wait(&tempty[acc], accph ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int ch = 0; ch < P.chunks; ++ch) {
+        mbar_wait(&a_full[as], aph);
+        tc_fence_after();
+        const uint64_t da_stage = descA0 + (uint64_t)(smemA16 + as * (PATCH_STRIDE >> 4));
+        uint64_t db_chunk = descB0 + (uint64_t)(smemB16 + (RESIDENT ? ch * 9 * (C::B_TILE >> 4) : 0));
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) {
+          if (!RESIDENT) {
+            mbar_wait(&b_full[bs], bph);
+            tc_fence_after();
+          }
+          if (lane == 0 && !(P.dbg & 4)) {
+            constexpr int kStepB = DGRAD ? (2048 >> 4) : (32 >> 4);
+            const int r = tp / 3, s3 = tp % 3;
+            // fprop: out(h,w) += x(h+r-1, w+s-1) -> patch row (r, s); dgrad: dy(h+1-r, w+1-s) -> patch row (2-r, 2-s)
+            const int shift16 = (DGRAD ? ((2 - r) * PW + (2 - s3)) : (r * PW + s3)) * 8;
+            const uint64_t db_tap = RESIDENT ? db_chunk + (uint64_t)(tp * (C::B_TILE >> 4))
+                                             : descB0 + (uint64_t)(smemB16 + bs * (C::B_TILE >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(d_tmem, da_stage + (uint64_t)(shift16 + k * 2), db_tap + (uint64_t)(k * kStepB), idesc,
+                          (ch > 0 || tp > 0 || k > 0) ? 1u : 0u);
+          }
+          if (!RESIDENT) {
+            if (lane == 0) umma_commit(&b_empty[bs]);
+            if (++bs == C::B_STAGES) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+        if (lane == 0) {
+          umma_commit(&a_empty[as]);
+          if (ch == P.chunks - 1) umma_commit(&tfull[acc]);
+        }
+        __syncwarp();
+        if (++as == a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0;
+    uint32_t accph = 0;
+    const bool stats = (!DGRAD) && P.sum != nullptr;
+    float stat_s[BN / 32], stat_q[BN / 32];
+#pragma unroll
+    for (int q = 0; q < BN / 32; ++q) stat_s[q] = stat_q[q] = 0.f;
+    for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
+      const int n = mt / (P.tiles_h * P.tiles_w);
+      const int rem = mt - n * (P.tiles_h * P.tiles_w);
+      const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+      const int m = quad * 32 + lane;  // accumulator row = 8*g + i  -> pixel (h0+g, w0+i)
+      const int h = th * TH + (m >> 3), w = tw * TW + (m & 7);
+      const bool valid = (h < P.H) && (w < P.W);
+      mbar_wait(&tfull[acc], accph);
+      tc_fence_after();
+      bf16* orow = reinterpret_cast<bf16*>(P.out) + (((long)n * P.H + h) * P.W + w) * P.Nout + n0;
+      uint32_t va[BN / 32][32];
+      if (!(P.dbg & 8)) {
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q)
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + q * 32, va[q]);
+        tmem_ld_wait();
+      }
+      // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the stores
+      tc_fence_before();
+      mbar_arrive(&tempty[acc]);
+#pragma unroll
+      for (int q = 0; q < BN / 32; ++q) {
+        const int c0 = q * 32;
+        uint32_t(&v)[32] = va[q];
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const uint32_t pk = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          const float2 back = unpack_bf16x2(pk);
+          f[j] = valid ? back.x : 0.f;       // statistics are taken over the rounded values bn_apply will read
+          f[j + 1] = valid ? back.y : 0.f;
+          v[j >> 1] = pk;
+        }
+        if (valid && !(P.dbg & 1)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(orow + c0 + j * 8) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+        }
+        if (stats) {
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
+          stat_s[q] += colsum_transpose_reduce(f, lane).x;   // lane L accumulates column c0+L over this CTA's tiles
+          stat_q[q] += colsum_transpose_reduce(sq, lane).x;
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) accph ^= 1;
+    }
+    if (stats) {  // one atomic per (warp, channel) for the whole kernel instead of one per tile
+#pragma unroll
+      for (int q = 0; q < BN / 32; ++q) {
+        atomicAdd(P.sum + n0 + q * 32 + lane, stat_s[q]);
+        atomicAdd(P.sumsq + n0 + q * 32 + lane, stat_q[q]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiledH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+PFN_encodeTiledH h_enc = nullptr;
+int h_sms = 0;
+std::mutex h_mu;
+
+int h_init() {
+  std::lock_guard<std::mutex> lk(h_mu);
+  if (h_enc) return 0;
+  cudaDriverEntryPointQueryResult q;
+  void* f = nullptr;
+  FD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q));
+  h_enc = (PFN_encodeTiledH)f;
+  int dev = 0;
+  FD_CUDA_CHECK(cudaGetDevice(&dev));
+  FD_CUDA_CHECK(cudaDeviceGetAttribute(&h_sms, cudaDevAttrMultiProcessorCount, dev));
+  return h_enc ? 0 : -1;
+}
+
+int map_patch(CUtensorMap* m, const void* base, int N, int H, int W, int C) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t st[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, PW, PH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = h_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, st, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("conv_halo: patch tensor map", __FILE__, (int)r);
+    return -1;
+  }
+  return 0;
+}
+int map_w(CUtensorMap* m, const void* base, long rows, long cols, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t st[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = h_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, st, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("conv_halo: weight tensor map", __FILE__, (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+template <int BN, bool DGRAD, bool RESIDENT>
+int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cudaStream_t s) {
+  using C = HCfg<BN, DGRAD, RESIDENT>;
+  const int resident_bytes = RESIDENT ? p.chunks * 9 * C::B_TILE : 0;
+  const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
+  int a_stages = (int)((227 * 1024 - 1024 - 512 - b_bytes) / PATCH_STRIDE);
+  if (a_stages > 6) a_stages = 6;
+  if (p.sum == nullptr && p.sumsq != nullptr) a_stages = 2;  // (debug hook, unused)
+  const int smem = a_stages * PATCH_STRIDE + b_bytes + 1024 + 512;
+  if (a_stages < 2 || smem > 227 * 1024) {
+    fd_set_error("conv_halo: shared memory budget exceeded", __FILE__, __LINE__);
+    return -1;
+  }
+  FD_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int grid = h_sms / p.n_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles;
+  if (grid > total) grid = total;
+  if (grid < p.n_tiles) grid = p.n_tiles;
+  conv_halo_kernel<BN, DGRAD, RESIDENT><<<grid, kThreads, smem, s>>>(a, b, p, resident_bytes, a_stages);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+template <bool DGRAD>
+int conv3x3_dispatch(const void* in, const void* w, void* out, float* sum, float* sumsq, int N, int H, int W, int Cin,
+                     int Cout, int wcols, int variant, cudaStream_t s) {
+  // in: [N,H,W,Cin] (x or dy), out: [N,H,W,Cout]; weight matrix rows: K_filter, cols: 9*C_filter (wcols = C_filter)
+  if (h_init()) return -1;
+  if (Cin % 64 || Cout % 64) {
+    fd_set_error("conv3x3: channels must be multiples of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  HParams p{};
+  p.N = N; p.H = H; p.W = W; p.Cred = Cin; p.Nout = Cout; p.chunks = Cin / 64;
+  p.tiles_h = (H + TH - 1) / TH; p.tiles_w = (W + TW - 1) / TW;
+  p.m_tiles = N * p.tiles_h * p.tiles_w;
+  p.wcols = wcols; p.out = out; p.sum = sum; p.sumsq = sumsq;
+  p.dbg = variant >> 8; variant &= 255;
+  // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
+  const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
+  const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048;
+  if (variant == 0) {
+    if (res64 <= budget) variant = 1;
+    else variant = (Cout % 128 == 0) ? 3 : 2;
+  }
+  const int bn = (variant == 3 || variant == 4) ? 128 : 64;
+  if (Cout % bn) {
+    fd_set_error("conv3x3: output channels not divisible by the N tile", __FILE__, __LINE__);
+    return -1;
+  }
+  p.n_tiles = Cout / bn;
+  CUtensorMap ma, mb;
+  if (map_patch(&ma, in, N, H, W, Cin)) return -1;
+  // fprop: rows = K (filter outputs), box rows = bn ; dgrad: rows = K (reduction), box rows = 64 (N-major tiles)
+  const long wrows = DGRAD ? Cin : Cout;
+  if (map_w(&mb, w, wrows, 9L * wcols, DGRAD ? 64 : bn)) return -1;
+  switch (variant) {
+    case 1: return launch_halo<64, DGRAD, true>(ma, mb, p, s);
+    case 2: return launch_halo<64, DGRAD, false>(ma, mb, p, s);
+    case 3: return launch_halo<128, DGRAD, false>(ma, mb, p, s);
+    case 4: return launch_halo<128, DGRAD, true>(ma, mb, p, s);
+  }
+  fd_set_error("conv3x3: bad variant", __FILE__, __LINE__);
+  return -1;
+}
+
+
+// ------------------------------------------------------------------------------------------ wgrad (halo)
+// dW[k,r,s,c] = sum_{n,h,w} dY[n,h,w,k] * X[n,h+r-1,w+s-1,c].  A CTA owns (k-tile of 128, c-chunk of 64, tap group)
+// and reduces over a slice of the spatial tiles.  Per spatial tile ONE dY tile (16x8 pixels x 128 k, M-major) and
+// ONE X patch (18x10 pixels x 64 c, N-major) are loaded; each tap of the group is the patch seen through a shifted
+// descriptor and accumulates into its own 64-column TMEM block (up to 5 taps = 320 columns, single-buffered: the
+// accumulation runs over the CTA's whole spatial slice, the epilogue runs once).  fp32 results are added to dW with
+// vector atomics (split-K over CTAs).
+constexpr int WG_A_BYTES = 128 * 128 * 2;  // two [128 pixel rows x 64 k] blocks (k halves of the M=128 tile)
+constexpr int WG_STAGE = WG_A_BYTES + PATCH_STRIDE;
+constexpr int WG_STAGES = 3;
+
+struct WParams {
+  int N, H, W, C, K;
+  int tiles_h, tiles_w, m_tiles;
+  int k_tiles, c_chunks, groups, splits;
+  float* dw;  // [K][9][C]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, const WParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * WG_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* tfull = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int i = 0; i < WG_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item: (split, group, c-chunk, k-tile)
+  int t = blockIdx.x;
+  const int kt = t % P.k_tiles; t /= P.k_tiles;
+  const int cc = t % P.c_chunks; t /= P.c_chunks;
+  const int grp = t % P.groups; t /= P.groups;
+  const int split = t;
+  const int tap0 = (P.groups == 1) ? 0 : (grp == 0 ? 0 : 5);
+  const int tap1 = (P.groups == 1) ? 9 : (grp == 0 ? 5 : 9);
+  const int ntap = tap1 - tap0;
+  const int mt0 = (int)(((long)P.m_tiles * split) / P.splits);
+  const int mt1 = (int)(((long)P.m_tiles * (split + 1)) / P.splits);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int mt = mt0; mt < mt1; ++mt) {
+        const int n = mt / (P.tiles_h * P.tiles_w);
+        const int rem = mt - n * (P.tiles_h * P.tiles_w);
+        const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+        const int h0 = th * TH, w0 = tw * TW;
+        mbar_wait(&empty[st], ph ^ 1);
+        uint8_t* a = smem + st * WG_STAGE;
+        mbar_arrive_expect_tx(&full[st], WG_A_BYTES + PATCH_BYTES);
+        tma_load_4d(a, &mapDY, &full[st], kt * 128, w0, h0, n);
+        tma_load_4d(a + 16384, &mapDY, &full[st], kt * 128 + 64, w0, h0, n);
+        tma_load_4d(a + WG_A_BYTES, &mapX, &full[st], cc * 64, w0 - 1, h0 - 1, n);
+        if (++st == WG_STAGES) {
+          st = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+    const uint64_t descA0 = umma_smem_desc(0, 16384, 1024, UMMA_LAYOUT_SW128);
+    const uint64_t descB0 = umma_smem_desc(0, 0, PW * 128, UMMA_LAYOUT_SW128);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mt = mt0; mt < mt1; ++mt) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint64_t da0 = descA0 + (uint64_t)(smem16 + st * (WG_STAGE >> 4));
+        const uint64_t db0 = descB0 + (uint64_t)(smem16 + st * (WG_STAGE >> 4) + (WG_A_BYTES >> 4));
+        const uint32_t accflag = (mt > mt0) ? 1u : 0u;
+#pragma unroll
+        for (int tpi = 0; tpi < 5; ++tpi) {
+          const int tp = tap0 + tpi;
+          if (tp < tap1) {
+            const int r = tp / 3, s3 = tp - r * 3;
+            const uint64_t db_tap = db0 + (uint64_t)((r * PW + s3) * 8);
+            const uint32_t d_tmem = tmem_base + tpi * 64;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)  // 16 pixels (two 8-pixel row groups) per UMMA_K
+              umma_f16_ss(d_tmem, da0 + (uint64_t)(j * (2048 >> 4)), db_tap + (uint64_t)(j * ((2 * PW * 128) >> 4)), idesc,
+                          (j > 0) ? 1u : accflag);
+          }
+        }
+        umma_commit(&empty[st]);
+        if (mt == mt1 - 1) umma_commit(tfull);
+      }
+      __syncwarp();
+      if (++st == WG_STAGES) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    if (mt1 > mt0) {
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int krow = kt * 128 + quad * 32 + lane;
+      for (int tp = tap0; tp < tap1; ++tp) {
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (tp - tap0) * 64 + c0, v);
+          tmem_ld_wait();
+          if (krow < P.K) {
+            float* o = P.dw + ((long)krow * 9 + tp) * P.C + cc * 64 + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              atomicAdd(reinterpret_cast<float4*>(o + j),
+                        make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                    __uint_as_float(v[j + 3])));
+          }
+        }
+      }
+    }
+  }
+  (void)ntap;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int map_tile4d(CUtensorMap* m, const void* base, int N, int H, int W, int C, int bw, int bh) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t st[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = h_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, st, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("conv_halo: 4d tensor map", __FILE__, (int)r);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
+                     cudaStream_t s) {
+  if (h_init()) return -1;
+  if (C % 64 || K % 64) {
+    fd_set_error("conv3x3_wgrad: channels must be multiples of 64", __FILE__, __LINE__);
+    return -1;
+  }
+  WParams p{};
+  p.N = N; p.H = H; p.W = W; p.C = C; p.K = K;
+  p.tiles_h = (H + TH - 1) / TH; p.tiles_w = (W + TW - 1) / TW;
+  p.m_tiles = N * p.tiles_h * p.tiles_w;
+  p.k_tiles = (K + 127) / 128; p.c_chunks = C / 64; p.groups = 2;
+  const int base = p.k_tiles * p.c_chunks * p.groups;
+  if (splits < 1) {
+    splits = h_sms / base;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.m_tiles) splits = p.m_tiles;
+  p.splits = splits;
+  p.dw = dw;
+  CUtensorMap mdy, mx;
+  if (map_tile4d(&mdy, dy, N, H, W, K, TW, TH)) return -1;
+  if (map_tile4d(&mx, x, N, H, W, C, PW, PH)) return -1;
+  const int smem = WG_STAGES * WG_STAGE + 1024 + 256;
+  FD_CUDA_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  wgrad_halo_kernel<<<base * splits, kThreads, smem, s>>>(mdy, mx, p);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K,
+                     int variant, cudaStream_t s) {
+  if (sum) {
+    FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, K * sizeof(float), s));
+    FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, K * sizeof(float), s));
+  }
+  return conv3x3_dispatch<false>(x, w, y, sum, sumsq, N, H, W, C, K, C, variant, s);
+}
+int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int variant,
+                     cudaStream_t s) {
+  return conv3x3_dispatch<true>(dy, w, dx, nullptr, nullptr, N, H, W, K, C, C, variant, s);
+}

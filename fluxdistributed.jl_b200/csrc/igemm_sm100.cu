@@ -183,6 +183,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     constexpr bool A_MN = (MODE == MODE_WGRAD);
     constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_WGRAD);
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    const uint64_t descA0 = A_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+    const uint64_t descB0 = B_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
+    const uint32_t smemA16 = smem_u32(smemA) >> 4, smemB16 = smem_u32(smemB) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
@@ -202,19 +205,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a_addr = smem_u32(smemA + stage * C::A_BYTES);
-          const uint32_t b_addr = smem_u32(smemB + stage * C::B_BYTES);
+          // K-major SW128: 8-row groups 1024B apart, advance 32B per UMMA_K inside the swizzle row.
+          // MN-major SW128: tile is [k rows][64 mn elems]; 8-k groups 1024B apart (SBO), 64-mn blocks
+          // BK*128B apart (LBO); advance 16 rows = 2048B per UMMA_K.  Descriptors = precomputed base + address
+          // field, so the single issuing thread spends ~3 instructions per MMA.
+          const uint64_t da0 = descA0 + (uint64_t)(smemA16 + stage * (C::A_BYTES >> 4));
+          const uint64_t db0 = descB0 + (uint64_t)(smemB16 + stage * (C::B_BYTES >> 4));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major SW128: 8-row groups 1024B apart, advance 32B per UMMA_K inside the swizzle row.
-            // MN-major SW128: tile is [k rows][64 mn elems]; 8-k groups 1024B apart (SBO), 64-mn blocks
-            // BK*128B apart (LBO); advance 16 rows = 2048B per UMMA_K.
-            const uint64_t da = A_MN ? umma_smem_desc(a_addr + k * 2048, BK * 128, 1024, UMMA_LAYOUT_SW128)
-                                     : umma_smem_desc(a_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            const uint64_t db = B_MN ? umma_smem_desc(b_addr + k * 2048, BK * 128, 1024, UMMA_LAYOUT_SW128)
-                                     : umma_smem_desc(b_addr + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16_ss(d_tmem, da0 + (uint64_t)(k * (A_MN ? 128 : 2)), db0 + (uint64_t)(k * (B_MN ? 128 : 2)), idesc,
+                        (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);                         // smem slot free once these MMAs retire
           if (kb == kb_count - 1) umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
         }

@@ -60,7 +60,22 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
   if (rl < RL) {
-    for (long r = (long)blockIdx.x * RL + rl; r < M; r += (long)gridDim.x * RL) {
+    // each block owns a contiguous slab of rows; 4 independent 16-byte loads in flight per thread
+    const long per = (M + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
+    long r = r0 + rl;
+    for (; r + 3L * RL < r1; r += 4L * RL) {
+      V8 v0 = ldg8(y + r * C + cv * 8), v1 = ldg8(y + (r + RL) * C + cv * 8), v2 = ldg8(y + (r + 2L * RL) * C + cv * 8),
+         v3 = ldg8(y + (r + 3L * RL) * C + cv * 8);
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(v0, f0); unpack8(v1, f1); unpack8(v2, f2); unpack8(v3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        acc[1][j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+      }
+    }
+    for (; r < r1; r += RL) {
       float f[8];
       unpack8(ldg8(y + r * C + cv * 8), f);
 #pragma unroll
@@ -145,7 +160,31 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, 
     rs[j] = rstd[cv * 8 + j];
   }
   if (rl < RL) {
-    for (long r = (long)blockIdx.x * RL + rl; r < M; r += (long)gridDim.x * RL) {
+    const long per = (M + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
+    long r = r0 + rl;
+    for (; r + RL < r1; r += 2L * RL) {  // two rows (six 16-byte loads) in flight per thread
+      const long o0 = r * C + cv * 8, o1 = (r + RL) * C + cv * 8;
+      V8 a0 = ldg8(dout + o0), a1 = ldg8(dout + o1), b0 = ldg8(y + o0), b1 = ldg8(y + o1), c0, c1;
+      if (relu) {
+        c0 = ldg8(out + o0);
+        c1 = ldg8(out + o1);
+      }
+      float d0[8], d1[8], y0[8], y1[8], q0[8], q1[8];
+      unpack8(a0, d0); unpack8(a1, d1); unpack8(b0, y0); unpack8(b1, y1);
+      if (relu) {
+        unpack8(c0, q0);
+        unpack8(c1, q1);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float z0 = (relu && !(q0[j] > 0.f)) ? 0.f : d0[j];
+        const float z1 = (relu && !(q1[j] > 0.f)) ? 0.f : d1[j];
+        acc[0][j] += (z0 * (y0[j] - mu[j]) + z1 * (y1[j] - mu[j])) * rs[j];
+        acc[1][j] += z0 + z1;
+      }
+    }
+    for (; r < r1; r += RL) {
       float d[8], yy[8], o[8];
       unpack8(ldg8(dout + r * C + cv * 8), d);
       unpack8(ldg8(y + r * C + cv * 8), yy);
@@ -521,7 +560,7 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
   if (RL == 0) { fd_set_error("bn_stats: C too large for this tiling", __FILE__, __LINE__); return -1; }
   FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, C * sizeof(float), s));
   FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, C * sizeof(float), s));
-  int grid = grid_for((M + RL - 1) / RL, 1, 148 * 8);
+  int grid = grid_for((M + 4L * RL - 1) / (4L * RL), 1, 148 * 6);
   size_t sm = (size_t)RL * C * 2 * sizeof(float);
   bn_stats_kernel<<<grid, 256, sm, s>>>(reinterpret_cast<const bf16*>(y), sum, sumsq, M, C);
   FD_LAUNCH_OK();
@@ -547,7 +586,7 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
   if (RL == 0) { fd_set_error("bn_bwd: C too large", __FILE__, __LINE__); return -1; }
   FD_CUDA_CHECK(cudaMemsetAsync(dgamma, 0, C * sizeof(float), s));
   FD_CUDA_CHECK(cudaMemsetAsync(dbeta, 0, C * sizeof(float), s));
-  int grid = grid_for((M + RL - 1) / RL, 1, 148 * 8);
+  int grid = grid_for((M + 2L * RL - 1) / (2L * RL), 1, 148 * 6);
   bn_bwd_reduce_kernel<<<grid, 256, (size_t)RL * C * 2 * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
       rstd, dgamma, dbeta, M, C, relu);

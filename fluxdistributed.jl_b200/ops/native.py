@@ -57,6 +57,42 @@ def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch
     return from_nhwc(y)
 
 
+def conv3x3_fprop(x: torch.Tensor, w: torch.Tensor, stats: bool = False, variant: int = 0):
+    """Halo-tile 3x3/stride-1/pad-1 forward conv; with ``stats`` also returns the per-channel
+    (sum, sum of squares) of the bf16 output accumulated in the epilogue (fused BN statistics)."""
+    xh, wk = nhwc(x), krsc(w)
+    n, h, ww, _ = xh.shape
+    k = wk.shape[0]
+    y = torch.empty(n, h, ww, k, dtype=BF16, device=x.device)
+    s = ss = None
+    if stats:
+        s = torch.empty(k, dtype=torch.float32, device=x.device)
+        ss = torch.empty(k, dtype=torch.float32, device=x.device)
+    _ext().conv3x3_fprop(xh, wk, y, s, ss, variant)
+    return (from_nhwc(y), s, ss) if stats else from_nhwc(y)
+
+
+def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, variant: int = 0) -> torch.Tensor:
+    dyh, wk = nhwc(dy), krsc(w)
+    n, h, ww, _ = dyh.shape
+    dx = torch.empty(n, h, ww, wk.shape[3], dtype=BF16, device=dy.device)
+    _ext().conv3x3_dgrad(dyh, wk, dx, variant)
+    return from_nhwc(dx)
+
+
+def conv3x3_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor] = None, splits: int = 0):
+    dyh, xh = nhwc(dy), nhwc(x)
+    k, c = dyh.shape[3], xh.shape[3]
+    if out is None:
+        buf = torch.zeros(k, 3, 3, c, dtype=torch.float32, device=dy.device)
+        _ext().conv3x3_wgrad(dyh, xh, buf, splits)
+        return buf.permute(0, 3, 1, 2)
+    buf = out.permute(0, 2, 3, 1)
+    assert buf.is_contiguous() and buf.dtype == torch.float32
+    _ext().conv3x3_wgrad(dyh, xh, buf, splits)
+    return out
+
+
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int) -> torch.Tensor:
     """Data gradient.  Stride 1 runs the tcgen05 dgrad directly; stride 2 zero-upsamples ``dy``
     (``dy_up[2i,2j] = dy[i,j]``) and reuses the stride-1 kernel."""
@@ -163,6 +199,13 @@ def _tc_ok(cin: int, cout: int) -> bool:
     return cin % 64 == 0 and cout % 64 == 0
 
 
+def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
+    """Per-shape kernel choice measured by scripts/conv_bench.py (profiles/conv_bench_r1.json): the halo kernel
+    wins when the filter slice is small enough to stay resident in shared memory and the image is large
+    (ResNet stage 1); the im2col-TMA kernel wins for the wide, small-image stages."""
+    return cred == 64 and cout == 64 and hw >= 28
+
+
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
@@ -172,7 +215,10 @@ class _ConvBNAct(torch.autograd.Function):
             wl = wl.contiguous(memory_format=torch.channels_last)
         x = x if x.dtype == BF16 else x.to(BF16)
         tc = _tc_ok(w.shape[1], w.shape[0])
-        if tc:
+        k3 = tc and w.shape[2] == 3 and w.shape[3] == 3 and stride == 1 and pad == 1
+        if k3 and _halo_fprop_ok(w.shape[1], w.shape[0], x.shape[2]):
+            y = conv3x3_fprop(x, wl)  # halo-tile kernel: one patch load serves all 9 taps
+        elif tc:
             y = conv_fprop(x, wl, stride, pad)
         else:  # C=3 stem: tensor-core tiling needs C%64==0 (space-to-depth stem is the planned native path)
             y = F.conv2d(x, wl, None, stride, pad)
@@ -183,14 +229,14 @@ class _ConvBNAct(torch.autograd.Function):
             s = ss = gamma  # unused
         out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
         ctx.save_for_backward(x, wl, y, out if relu else None, mean, rstd, gamma)
-        ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape))
+        ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape), k3)
         ctx.w_gradbuf, ctx.g_gradbuf, ctx.b_gradbuf = w_gradbuf if isinstance(w_gradbuf, tuple) else (w_gradbuf, None, None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, wl, y, out, mean, rstd, gamma = ctx.saved_tensors
-        relu, stride, pad, has_res, tc, w_shape, x_shape = ctx.cfg
+        relu, stride, pad, has_res, tc, w_shape, x_shape, k3 = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
         dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
                                          dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
@@ -198,11 +244,15 @@ class _ConvBNAct(torch.autograd.Function):
             dgamma = dbeta = None
         dx = None
         if ctx.needs_input_grad[0]:
-            if tc:
+            if k3 and _halo_fprop_ok(w_shape[0], w_shape[1], x_shape[2]):
+                dx = conv3x3_dgrad(dy, wl)
+            elif tc:
                 dx = conv_dgrad(dy, wl, x_shape, stride, pad)
             else:
                 dx = torch.nn.grad.conv2d_input(x_shape, wl, dy, stride, pad)
-        if tc:
+        if k3 and x_shape[2] >= 14:
+            gw = conv3x3_wgrad(dy, x, out=ctx.w_gradbuf)
+        elif tc:
             gw = conv_wgrad(dy, x, w_shape, stride, pad, out=ctx.w_gradbuf)
         else:
             gw = torch.nn.grad.conv2d_weight(x.float(), w_shape, dy.float(), stride, pad)

@@ -87,6 +87,54 @@ def test_conv_wgrad(N, H, W, C, K, R, stride, pad):
     assert rel_err(dw, ref) < 1e-2
 
 
+HALO_CASES = [
+    # N, H, W, C, K
+    (2, 16, 8, 64, 64),
+    (3, 56, 56, 64, 64),
+    (2, 28, 28, 128, 128),
+    (2, 14, 14, 256, 256),
+    (4, 7, 7, 512, 512),
+    (2, 20, 13, 64, 128),
+]
+
+
+@pytest.mark.parametrize("N,H,W,C,K", HALO_CASES)
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_halo_fprop_and_stats(N, H, W, C, K, variant):
+    if variant == 1 and C > 128:
+        pytest.skip("resident filter slice does not fit")
+    if variant == 3 and K % 128:
+        pytest.skip("BN=128 needs K%128==0")
+    x, w = _conv_data(N, H, W, C, K, 3)
+    y, s, ss = ops.conv3x3_fprop(x, w, stats=True, variant=variant)
+    ref = REF.conv_fprop_ref(x, w, 1, 1)
+    assert rel_err(y, ref) < 1e-2
+    yf = y.float()
+    assert rel_err(s, yf.sum(dim=(0, 2, 3))) < 1e-3
+    assert rel_err(ss, (yf * yf).sum(dim=(0, 2, 3))) < 1e-3
+
+
+@pytest.mark.parametrize("N,H,W,C,K", HALO_CASES)
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_halo_dgrad(N, H, W, C, K, variant):
+    if variant == 3 and C % 128:
+        pytest.skip("BN=128 needs C%128==0")
+    x, w = _conv_data(N, H, W, C, K, 3)
+    dy = cl(torch.randn(N, K, H, W, device="cuda").to(BF))
+    dx = ops.conv3x3_dgrad(dy, w, variant=variant)
+    ref = REF.conv_dgrad_ref(dy, w, (N, C, H, W), 1, 1)
+    assert rel_err(dx, ref) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W,C,K", HALO_CASES)
+def test_halo_wgrad(N, H, W, C, K):
+    x, w = _conv_data(N, H, W, C, K, 3)
+    dy = cl(torch.randn(N, K, H, W, device="cuda").to(BF))
+    dw = ops.conv3x3_wgrad(dy, x)
+    ref = REF.conv_wgrad_ref(dy, x, (K, C, 3, 3), 1, 1)
+    assert rel_err(dw, ref) < 1e-2
+
+
 @pytest.mark.parametrize("C,relu,res", [(64, True, False), (128, True, True), (512, False, False)])
 def test_bn_fwd_bwd(C, relu, res):
     y = cl((torch.randn(6, C, 10, 10, device="cuda") * 2 + 0.5).to(BF))
