@@ -15,7 +15,7 @@
 const char* fd_last_error();
 long fd_launch_count();
 int fd_probe_shift32(const void* A, const void* B, float* D, int rows, int shift, int sbo, int mn_major, cudaStream_t s);
-int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, cudaStream_t s);
+int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, int grid, int flavor, cudaStream_t s);
 int fd_probe_shift(const void* A, const void* B, float* D, int rows, int shift, int sbo, int base_off, int mn_major,
                    int nk16, cudaStream_t s);
 
@@ -286,9 +286,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_probe_shift32(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, mn_major, cur_stream()),
           "probe_shift32");
   });
-  m.def("probe_mma_rate", [](at::Tensor out, int bn, int reps, int shift, int sbo) {
+  m.def("probe_mma_rate", [](at::Tensor out, int bn, int reps, int shift, int sbo, int grid, int flavor) {
     c10::cuda::CUDAGuard guard(out.device());
-    check(fd_probe_mma_rate(reinterpret_cast<long long*>(out.data_ptr<int64_t>()), bn, reps, shift, sbo, cur_stream()), "probe_mma_rate");
+    check(fd_probe_mma_rate(reinterpret_cast<long long*>(out.data_ptr<int64_t>()), bn, reps, shift, sbo, grid, flavor, cur_stream()), "probe_mma_rate");
   });
   m.def("probe_shift", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, int base_off, bool mn_major, int nk16) {
     c10::cuda::CUDAGuard guard(A.device());

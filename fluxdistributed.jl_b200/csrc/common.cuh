@@ -227,6 +227,71 @@ FD_DEVINL constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b
          | ((uint32_t)(M >> 4) << 24);   // m_dim
 }
 
+// ---- predicated single-lane issue from CONVERGENT code -------------------------------------------------------
+// tcgen05.mma / commit / TMA take their operands from uniform registers.  Issuing them under `if (lane == 0)` puts
+// them in a divergent region where the compiler must assume per-thread values and wraps each one in an
+// ELECT + R2UR.BROADCAST loop (~19 SASS instructions per MMA; see profiles/).  Keeping the warp convergent and
+// predicating the instruction itself (`@q`) lets descriptors live in uniform registers: ~3 instructions per MMA.
+FD_DEVINL void umma_f16_ss_p(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate,
+                             uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(issue)
+      : "memory");
+}
+FD_DEVINL void umma_commit_p(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
+FD_DEVINL void mbar_arrive_expect_tx_p(uint64_t* bar, uint32_t bytes, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(issue)
+      : "memory");
+}
+FD_DEVINL void mbar_arrive_p(uint64_t* bar, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(issue)
+      : "memory");
+}
+FD_DEVINL void tma_load_2d_p(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      "\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(issue)
+      : "memory");
+}
+FD_DEVINL void tma_load_4d_p(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3,
+                             uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2];\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(issue)
+      : "memory");
+}
+FD_DEVINL void tma_load_im2col_4d_p(void* smem_dst, const void* desc, uint64_t* bar, int c, int w, int h, int n,
+                                    uint16_t off_w, uint16_t off_h, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %9, 0;\n\t"
+      "@q cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, "
+      "%6}], [%2], {%7, %8};\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "r"(issue)
+      : "memory");
+}
+// warp-uniform broadcast of a value every lane already holds (tells the compiler it is uniform)
+FD_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 FD_DEVINL bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -84,7 +84,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* tempty = bars + 34;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t leader = (lane == 0) ? 1u : 0u;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapB);
@@ -109,7 +110,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // each CTA serves one output-channel tile (so a resident filter slice stays valid) and strides over m-tiles
   const int nt = blockIdx.x % P.n_tiles;
@@ -119,56 +120,55 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int taps = 9;
 
   if (warp == 0) {
-    if (lane == 0) {
-      if (RESIDENT) {
-        mbar_arrive_expect_tx(&b_full[0], resident_bytes);
-        for (int ch = 0; ch < P.chunks; ++ch)
+    // producer: the whole warp walks the schedule (convergent), lane 0 issues the copies (predicated PTX)
+    if (RESIDENT) {
+      mbar_arrive_expect_tx_p(&b_full[0], resident_bytes, leader);
+      for (int ch = 0; ch < P.chunks; ++ch)
+        for (int tp = 0; tp < taps; ++tp) {
+          uint8_t* dst = smemB + (ch * taps + tp) * C::B_TILE;
+          if (!DGRAD) {
+            tma_load_2d_p(dst, &mapB, &b_full[0], tp * P.wcols + ch * 64, n0, leader);
+          } else {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_p(dst + j * 8192, &mapB, &b_full[0], tp * P.wcols + n0 + j * 64, ch * 64, leader);
+          }
+        }
+    }
+    int as = 0, bs = 0;
+    uint32_t aph = 0, bph = 0;
+    for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
+      const int n = mt / (P.tiles_h * P.tiles_w);
+      const int rem = mt - n * (P.tiles_h * P.tiles_w);
+      const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+      const int h0 = th * TH, w0 = tw * TW;
+      for (int ch = 0; ch < P.chunks; ++ch) {
+        mbar_wait(&a_empty[as], aph ^ 1);
+        if (P.dbg & 2) {
+          mbar_arrive_p(&a_full[as], leader);
+        } else {
+          mbar_arrive_expect_tx_p(&a_full[as], PATCH_BYTES, leader);
+          tma_load_4d_p(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], ch * 64, w0 - 1, h0 - 1, n, leader);
+        }
+        if (++as == a_stages) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (!RESIDENT) {
           for (int tp = 0; tp < taps; ++tp) {
-            uint8_t* dst = smemB + (ch * taps + tp) * C::B_TILE;
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_arrive_expect_tx_p(&b_full[bs], C::B_TILE, leader);
+            uint8_t* dst = smemB + bs * C::B_TILE;
             if (!DGRAD) {
-              tma_load_2d(dst, &mapB, &b_full[0], tp * P.wcols + ch * 64, n0);
+              tma_load_2d_p(dst, &mapB, &b_full[bs], tp * P.wcols + ch * 64, n0, leader);
             } else {
 #pragma unroll
               for (int j = 0; j < BN / 64; ++j)
-                tma_load_2d(dst + j * 8192, &mapB, &b_full[0], tp * P.wcols + n0 + j * 64, ch * 64);
+                tma_load_2d_p(dst + j * 8192, &mapB, &b_full[bs], tp * P.wcols + n0 + j * 64, ch * 64, leader);
             }
-          }
-      }
-      int as = 0, bs = 0;
-      uint32_t aph = 0, bph = 0;
-      for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
-        const int n = mt / (P.tiles_h * P.tiles_w);
-        const int rem = mt - n * (P.tiles_h * P.tiles_w);
-        const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
-        const int h0 = th * TH, w0 = tw * TW;
-        for (int ch = 0; ch < P.chunks; ++ch) {
-          mbar_wait(&a_empty[as], aph ^ 1);
-          if (P.dbg & 2) {
-            mbar_arrive(&a_full[as]);
-          } else {
-            mbar_arrive_expect_tx(&a_full[as], PATCH_BYTES);
-            tma_load_4d(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], ch * 64, w0 - 1, h0 - 1, n);
-          }
-          if (++as == a_stages) {
-            as = 0;
-            aph ^= 1;
-          }
-          if (!RESIDENT) {
-            for (int tp = 0; tp < taps; ++tp) {
-              mbar_wait(&b_empty[bs], bph ^ 1);
-              mbar_arrive_expect_tx(&b_full[bs], C::B_TILE);
-              uint8_t* dst = smemB + bs * C::B_TILE;
-              if (!DGRAD) {
-                tma_load_2d(dst, &mapB, &b_full[bs], tp * P.wcols + ch * 64, n0);
-              } else {
-#pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                  tma_load_2d(dst + j * 8192, &mapB, &b_full[bs], tp * P.wcols + n0 + j * 64, ch * 64);
-              }
-              if (++bs == (RESIDENT ? 1 : C::B_STAGES)) {
-                bs = 0;
-                bph ^= 1;
-              }
+            if (++bs == (RESIDENT ? 1 : C::B_STAGES)) {
+              bs = 0;
+              bph ^= 1;
             }
           }
         }
@@ -204,7 +204,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
           }
-          if (lane == 0 && !(P.dbg & 4)) {
+          {
+            const uint32_t go = (P.dbg & 4) ? 0u : leader;
             constexpr int kStepB = DGRAD ? (2048 >> 4) : (32 >> 4);
             const int r = tp / 3, s3 = tp % 3;
             // fprop: out(h,w) += x(h+r-1, w+s-1) -> patch row (r, s); dgrad: dy(h+1-r, w+1-s) -> patch row (2-r, 2-s)
@@ -213,22 +214,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                              : descB0 + (uint64_t)(smemB16 + bs * (C::B_TILE >> 4));
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_f16_ss(d_tmem, da_stage + (uint64_t)(shift16 + k * 2), db_tap + (uint64_t)(k * kStepB), idesc,
-                          (ch > 0 || tp > 0 || k > 0) ? 1u : 0u);
+              umma_f16_ss_p(d_tmem, da_stage + (uint64_t)(shift16 + k * 2), db_tap + (uint64_t)(k * kStepB), idesc,
+                            (ch > 0 || tp > 0 || k > 0) ? 1u : 0u, go);
           }
           if (!RESIDENT) {
-            if (lane == 0) umma_commit(&b_empty[bs]);
+            umma_commit_p(&b_empty[bs], leader);
             if (++bs == C::B_STAGES) {
               bs = 0;
               bph ^= 1;
             }
           }
         }
-        if (lane == 0) {
-          umma_commit(&a_empty[as]);
-          if (ch == P.chunks - 1) umma_commit(&tfull[acc]);
-        }
-        __syncwarp();
+        umma_commit_p(&a_empty[as], leader);
+        if (ch == P.chunks - 1) umma_commit_p(&tfull[acc], leader);
         if (++as == a_stages) {
           as = 0;
           aph ^= 1;
@@ -454,7 +452,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
   uint64_t* empty = bars + 4;
   uint64_t* tfull = bars + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t leader = (lane == 0) ? 1u : 0u;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapDY);
     tma_prefetch_desc(&mapX);
@@ -472,7 +471,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   // work item: (split, group, c-chunk, k-tile)
   int t = blockIdx.x;
@@ -487,24 +486,22 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
   const int mt1 = (int)(((long)P.m_tiles * (split + 1)) / P.splits);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int st = 0;
-      uint32_t ph = 0;
-      for (int mt = mt0; mt < mt1; ++mt) {
-        const int n = mt / (P.tiles_h * P.tiles_w);
-        const int rem = mt - n * (P.tiles_h * P.tiles_w);
-        const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
-        const int h0 = th * TH, w0 = tw * TW;
-        mbar_wait(&empty[st], ph ^ 1);
-        uint8_t* a = smem + st * WG_STAGE;
-        mbar_arrive_expect_tx(&full[st], WG_A_BYTES + PATCH_BYTES);
-        tma_load_4d(a, &mapDY, &full[st], kt * 128, w0, h0, n);
-        tma_load_4d(a + 16384, &mapDY, &full[st], kt * 128 + 64, w0, h0, n);
-        tma_load_4d(a + WG_A_BYTES, &mapX, &full[st], cc * 64, w0 - 1, h0 - 1, n);
-        if (++st == WG_STAGES) {
-          st = 0;
-          ph ^= 1;
-        }
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mt = mt0; mt < mt1; ++mt) {
+      const int n = mt / (P.tiles_h * P.tiles_w);
+      const int rem = mt - n * (P.tiles_h * P.tiles_w);
+      const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+      const int h0 = th * TH, w0 = tw * TW;
+      mbar_wait(&empty[st], ph ^ 1);
+      uint8_t* a = smem + st * WG_STAGE;
+      mbar_arrive_expect_tx_p(&full[st], WG_A_BYTES + PATCH_BYTES, leader);
+      tma_load_4d_p(a, &mapDY, &full[st], kt * 128, w0, h0, n, leader);
+      tma_load_4d_p(a + 16384, &mapDY, &full[st], kt * 128 + 64, w0, h0, n, leader);
+      tma_load_4d_p(a + WG_A_BYTES, &mapX, &full[st], cc * 64, w0 - 1, h0 - 1, n, leader);
+      if (++st == WG_STAGES) {
+        st = 0;
+        ph ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -517,7 +514,7 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
     for (int mt = mt0; mt < mt1; ++mt) {
       mbar_wait(&full[st], ph);
       tc_fence_after();
-      if (lane == 0) {
+      {
         const uint64_t da0 = descA0 + (uint64_t)(smem16 + st * (WG_STAGE >> 4));
         const uint64_t db0 = descB0 + (uint64_t)(smem16 + st * (WG_STAGE >> 4) + (WG_A_BYTES >> 4));
         const uint32_t accflag = (mt > mt0) ? 1u : 0u;
@@ -530,14 +527,13 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
             const uint32_t d_tmem = tmem_base + tpi * 64;
 #pragma unroll
             for (int j = 0; j < 8; ++j)  // 16 pixels (two 8-pixel row groups) per UMMA_K
-              umma_f16_ss(d_tmem, da0 + (uint64_t)(j * (2048 >> 4)), db_tap + (uint64_t)(j * ((2 * PW * 128) >> 4)), idesc,
-                          (j > 0) ? 1u : accflag);
+              umma_f16_ss_p(d_tmem, da0 + (uint64_t)(j * (2048 >> 4)), db_tap + (uint64_t)(j * ((2 * PW * 128) >> 4)), idesc,
+                            (j > 0) ? 1u : accflag, leader);
           }
         }
-        umma_commit(&empty[st]);
-        if (mt == mt1 - 1) umma_commit(tfull);
+        umma_commit_p(&empty[st], leader);
+        if (mt == mt1 - 1) umma_commit_p(tfull, leader);
       }
-      __syncwarp();
       if (++st == WG_STAGES) {
         st = 0;
         ph ^= 1;

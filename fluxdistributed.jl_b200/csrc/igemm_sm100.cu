@@ -82,8 +82,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   uint64_t* tempty = bars + 2 * kStages + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = (int)uniform_u32(threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const uint32_t leader = (lane == 0) ? 1u : 0u;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -105,13 +106,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
   const int total_tiles = P.m_tiles * P.n_tiles * P.splits;
 
   if (warp == 0) {
-    // ===================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================== TMA producer (convergent warp, lane 0 issues)
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -140,24 +141,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* a = smemA + stage * C::A_BYTES;
           uint8_t* b = smemB + stage * C::B_BYTES;
-          mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+          mbar_arrive_expect_tx_p(&full[stage], C::STAGE_BYTES, leader);
           if (MODE == MODE_GEMM) {
-            tma_load_2d(a, &mapA, &full[stage], kb * BK, m0);
-            tma_load_2d(b, &mapB, &full[stage], kb * BK, n0);
+            tma_load_2d_p(a, &mapA, &full[stage], kb * BK, m0, leader);
+            tma_load_2d_p(b, &mapB, &full[stage], kb * BK, n0, leader);
           } else if (MODE == MODE_FPROP) {
             const int tp = kb / P.C_chunks, cc = kb - tp * P.C_chunks;
             const int r = tp / P.S, s = tp - r * P.S;
-            tma_load_im2col_4d(a, &mapA, &full[stage], cc * BK, bw, bh, bn, (uint16_t)s, (uint16_t)r);
-            tma_load_2d(b, &mapB, &full[stage], tp * P.Ctot + cc * BK, n0);
+            tma_load_im2col_4d_p(a, &mapA, &full[stage], cc * BK, bw, bh, bn, (uint16_t)s, (uint16_t)r, leader);
+            tma_load_2d_p(b, &mapB, &full[stage], tp * P.Ctot + cc * BK, n0, leader);
           } else if (MODE == MODE_DGRAD) {
             // reduction over (tap, k-chunk); A = im2col(dY) with flipped taps, B = W[k, (r,s,c)] (N-major)
             const int tp = kb / P.C_chunks, kc = kb - tp * P.C_chunks;
             const int r = tp / P.S, s = tp - r * P.S;
-            tma_load_im2col_4d(a, &mapA, &full[stage], kc * BK, bw, bh, bn, (uint16_t)(P.S - 1 - s),
-                               (uint16_t)(P.R - 1 - r));
+            tma_load_im2col_4d_p(a, &mapA, &full[stage], kc * BK, bw, bh, bn, (uint16_t)(P.S - 1 - s),
+                                 (uint16_t)(P.R - 1 - r), leader);
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(b + j * (BK * 128), &mapB, &full[stage], tp * P.Ctot + n0 + j * 64, kc * BK);
+              tma_load_2d_p(b + j * (BK * 128), &mapB, &full[stage], tp * P.Ctot + n0 + j * 64, kc * BK, leader);
           } else {  // WGRAD: A = dY[pixels, k] (M-major), B = im2col(X)[pixels, c] (N-major), both 64-pixel k-blocks
             const int cc = nt - tap * P.C_chunks;
             const int r = tap / P.S, s = tap - r * P.S;
@@ -167,9 +168,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             int p = r2 / P.Q, q = r2 - p * P.Q;
 #pragma unroll
             for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(a + j * (BK * 128), &mapA, &full[stage], m0 + j * 64, pix0);
-            tma_load_im2col_4d(b, &mapB, &full[stage], cc * BN, P.lower_w + q * P.stride, P.lower_h + p * P.stride, pn,
-                               (uint16_t)s, (uint16_t)r);
+              tma_load_2d_p(a + j * (BK * 128), &mapA, &full[stage], m0 + j * 64, pix0, leader);
+            tma_load_im2col_4d_p(b, &mapB, &full[stage], cc * BN, P.lower_w + q * P.stride, P.lower_h + p * P.stride, pn,
+                                 (uint16_t)s, (uint16_t)r, leader);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -204,7 +205,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       for (int kb = 0; kb < kb_count; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        {
           // K-major SW128: 8-row groups 1024B apart, advance 32B per UMMA_K inside the swizzle row.
           // MN-major SW128: tile is [k rows][64 mn elems]; 8-k groups 1024B apart (SBO), 64-mn blocks
           // BK*128B apart (LBO); advance 16 rows = 2048B per UMMA_K.  Descriptors = precomputed base + address
@@ -213,18 +214,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const uint64_t db0 = descB0 + (uint64_t)(smemB16 + stage * (C::B_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_f16_ss(d_tmem, da0 + (uint64_t)(k * (A_MN ? 128 : 2)), db0 + (uint64_t)(k * (B_MN ? 128 : 2)), idesc,
-                        (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[stage]);                         // smem slot free once these MMAs retire
-          if (kb == kb_count - 1) umma_commit(&tfull[acc]);   // accumulator ready for the epilogue
+            umma_f16_ss_p(d_tmem, da0 + (uint64_t)(k * (A_MN ? 128 : 2)), db0 + (uint64_t)(k * (B_MN ? 128 : 2)), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u, leader);
+          umma_commit_p(&empty[stage], leader);                         // smem slot free once these MMAs retire
+          if (kb == kb_count - 1) umma_commit_p(&tfull[acc], leader);   // accumulator ready for the epilogue
         }
-        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
-      if (kb_count == 0 && lane == 0) umma_commit(&tfull[acc]);
+      if (kb_count == 0) umma_commit_p(&tfull[acc], leader);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }

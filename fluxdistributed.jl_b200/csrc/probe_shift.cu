@@ -130,19 +130,19 @@ probe32_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
 // Timing probe: cycles for `reps` back-to-back tcgen05.mma (M=128, N=BN, K=16) with a given A start shift / SBO.
 template <int BN>
-__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int reps, int shift, int sbo) {
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int reps, int shift, int sbo, int flavor) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 96 * 1024);
+  uint64_t* done = reinterpret_cast<uint64_t*>(smem + 196 * 1024);
   uint32_t* slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+  for (int i = threadIdx.x; i < 196 * 1024 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
   if (threadIdx.x == 0) {
     mbar_init(done, 1);
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(slot, 256);
+    tmem_alloc(slot, 512);
     tmem_relinquish();
   }
   fence_proxy_async();
@@ -152,38 +152,58 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int re
   const uint32_t tm = *slot;
   if (threadIdx.x == 0) {
     const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    const uint32_t a = smem_u32(smem), b = smem_u32(smem + 48 * 1024);
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem + 32 * 1024);
     long long t0 = clock64();
+    uint32_t ph = 0;
     for (int r = 0; r < reps; ++r) {
+      // flavor bit0: alternate accumulator buffers every 9 groups; bit1: commit + wait every 9 groups (tile boundary)
+      const uint32_t d = tm + (((flavor & 1) && ((r / 9) & 1)) ? BN : 0);
+      const int tapshift = (flavor & 4) ? ((r % 9) / 3 * 10 + (r % 3)) : 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        uint64_t da = umma_smem_desc(a + shift * 128 + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
-        uint64_t db = umma_smem_desc(b + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
-        umma_f16_ss(tm, da, db, idesc, 1u);
+        uint64_t da = umma_smem_desc(a + (shift + tapshift) * 128 + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
+        uint64_t db = umma_smem_desc(b + ((flavor & 4) ? (r % 9) * BN * 128 : 0) + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        umma_f16_ss(d, da, db, idesc, (r % 9 == 0 && k == 0) ? 0u : 1u);
+      }
+      if ((flavor & 2) && (r % 9 == 8)) {
+        umma_commit(done);
+        if (flavor & 8) {
+          mbar_wait(done, ph);
+          ph ^= 1;
+        }
       }
     }
-    umma_commit(done);
-    mbar_wait(done, 0);
+    if (!(flavor & 8)) {
+      umma_commit(done);
+      // only the final phase is awaited when commits were issued without waiting: count completions
+    }
+    if (!(flavor & 2) || (flavor & 8)) {
+      if (!(flavor & 8)) mbar_wait(done, 0);
+    } else {
+      // (reps/9 + 1) arrivals on a count-1 barrier: wait for each phase in turn
+      const int n = reps / 9 + 1;
+      for (int i = 0; i < n; ++i) mbar_wait(done, i & 1);
+    }
     long long t1 = clock64();
-    out[0] = t1 - t0;
+    out[blockIdx.x] = t1 - t0;
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tm, 256);
+  if (warp == 0) tmem_dealloc(tm, 512);
 }
 
 }  // namespace
 
-int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, cudaStream_t s) {
-  const int smem = 100 * 1024;
+int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, int grid, int flavor, cudaStream_t s) {
+  const int smem = 200 * 1024;
   if (bn == 64) {
     FD_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<64><<<1, 128, smem, s>>>(out, reps, shift, sbo);
+    mma_rate_kernel<64><<<grid, 128, smem, s>>>(out, reps, shift, sbo, flavor);
   } else if (bn == 128) {
     FD_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<128><<<1, 128, smem, s>>>(out, reps, shift, sbo);
+    mma_rate_kernel<128><<<grid, 128, smem, s>>>(out, reps, shift, sbo, flavor);
   } else {
     FD_CUDA_CHECK(cudaFuncSetAttribute(mma_rate_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    mma_rate_kernel<256><<<1, 128, smem, s>>>(out, reps, shift, sbo);
+    mma_rate_kernel<256><<<grid, 128, smem, s>>>(out, reps, shift, sbo, flavor);
   }
   FD_LAUNCH_OK();
   return 0;
