@@ -262,6 +262,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
                            (int)x.size(3), (int)dy.size(3), splits, cur_stream()), "conv3x3_wgrad");
   });
+  m.def("s2d_pad", [](at::Tensor x, at::Tensor x2, int pad) {
+    c10::cuda::CUDAGuard guard(x.device());
+    check(fd_s2d_pad(x.data_ptr(), x2.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), pad, cur_stream()), "s2d_pad");
+  });
+  m.def("stem_w_s2d", [](at::Tensor w, at::Tensor w2) {
+    c10::cuda::CUDAGuard guard(w.device());
+    check(fd_stem_w_s2d(w.data_ptr(), w2.data_ptr(), (int)w.size(0), cur_stream()), "stem_w_s2d");
+  });
+  m.def("stem_dw_from_s2d", [](at::Tensor dw2, at::Tensor dw) {
+    c10::cuda::CUDAGuard guard(dw.device());
+    check(fd_stem_dw_from_s2d(dw2.data_ptr<float>(), dw.data_ptr<float>(), (int)dw.size(0), cur_stream()), "stem_dw_from_s2d");
+  });
+  m.def("stem_fprop", [](at::Tensor x2, at::Tensor w2, at::Tensor y, c10::optional<at::Tensor> sum, c10::optional<at::Tensor> sumsq) {
+    c10::cuda::CUDAGuard guard(x2.device());
+    check(fd_stem_fprop(x2.data_ptr(), w2.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x2.size(0), (int)x2.size(1),
+                        (int)x2.size(2), cur_stream()), "stem_fprop");
+  });
+  m.def("stem_wgrad", [](at::Tensor dy, at::Tensor x2, at::Tensor dw2) {
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_stem_wgrad(dy.data_ptr(), x2.data_ptr(), dw2.data_ptr<float>(), (int)x2.size(0), (int)x2.size(1), (int)x2.size(2),
+                        cur_stream()), "stem_wgrad");
+  });
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd", &bn_bwd);

@@ -65,7 +65,7 @@ FD_DEVINL float2 colsum_transpose_reduce(float (&v)[32], int lane) {
   return make_float2(v[0], 0.f);
 }
 
-template <int BN, bool DGRAD, bool RESIDENT>
+template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HParams P,
                  const int resident_bytes, const int a_stages) {
@@ -117,7 +117,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int n0 = nt * BN;
   const int m_first = blockIdx.x / P.n_tiles;
   const int m_step = gridDim.x / P.n_tiles;
-  const int taps = 9;
+  // STEM: the 7x7/2 stem as a 4x4/1 conv over the space-to-depth input; the A tile of filter row `a` is a plain
+  // [128 pixel x 64 (4 taps x 16 ch)] K-major tile fetched through an overlapping-stride tensor map, so each of the
+  // 4 'chunks' is one ordinary k-block (one tap, no shift).
+  constexpr int taps = STEM ? 1 : 9;
+  constexpr int A_BYTES = STEM ? 16384 : PATCH_BYTES;
 
   if (warp == 0) {
     // producer: the whole warp walks the schedule (convergent), lane 0 issues the copies (predicated PTX)
@@ -127,7 +131,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int tp = 0; tp < taps; ++tp) {
           uint8_t* dst = smemB + (ch * taps + tp) * C::B_TILE;
           if (!DGRAD) {
-            tma_load_2d_p(dst, &mapB, &b_full[0], tp * P.wcols + ch * 64, n0, leader);
+            tma_load_2d_p(dst, &mapB, &b_full[0], STEM ? ch * 64 : tp * P.wcols + ch * 64, n0, leader);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
@@ -147,8 +151,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (P.dbg & 2) {
           mbar_arrive_p(&a_full[as], leader);
         } else {
-          mbar_arrive_expect_tx_p(&a_full[as], PATCH_BYTES, leader);
-          tma_load_4d_p(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], ch * 64, w0 - 1, h0 - 1, n, leader);
+          mbar_arrive_expect_tx_p(&a_full[as], A_BYTES, leader);
+          if (STEM)
+            tma_load_4d_p(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], 0, w0, h0 + ch, n, leader);
+          else
+            tma_load_4d_p(smemA + as * PATCH_STRIDE, &mapA, &a_full[as], ch * 64, w0 - 1, h0 - 1, n, leader);
         }
         if (++as == a_stages) {
           as = 0;
@@ -179,7 +186,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     // shared-memory descriptors are a precomputed 64-bit base plus a 14-bit address field, and the tap / k offsets
     // are compile-time immediates of the fully unrolled 9 x 4 loop.
     constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, DGRAD ? 1 : 0);
-    const uint64_t descA0 = umma_smem_desc(0, 16, PW * 128, UMMA_LAYOUT_SW128);
+    const uint64_t descA0 = umma_smem_desc(0, 16, STEM ? 1024 : PW * 128, UMMA_LAYOUT_SW128);
     const uint64_t descB0 = DGRAD ? umma_smem_desc(0, 8192, 1024, UMMA_LAYOUT_SW128)
                                   : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
     int as = 0, bs = 0, acc = 0;
@@ -197,9 +204,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         mbar_wait(&a_full[as], aph);
         tc_fence_after();
         const uint64_t da_stage = descA0 + (uint64_t)(smemA16 + as * (PATCH_STRIDE >> 4));
-        uint64_t db_chunk = descB0 + (uint64_t)(smemB16 + (RESIDENT ? ch * 9 * (C::B_TILE >> 4) : 0));
+        uint64_t db_chunk = descB0 + (uint64_t)(smemB16 + (RESIDENT ? ch * taps * (C::B_TILE >> 4) : 0));
 #pragma unroll
-        for (int tp = 0; tp < 9; ++tp) {
+        for (int tp = 0; tp < taps; ++tp) {
           if (!RESIDENT) {
             mbar_wait(&b_full[bs], bph);
             tc_fence_after();
@@ -209,7 +216,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             constexpr int kStepB = DGRAD ? (2048 >> 4) : (32 >> 4);
             const int r = tp / 3, s3 = tp % 3;
             // fprop: out(h,w) += x(h+r-1, w+s-1) -> patch row (r, s); dgrad: dy(h+1-r, w+1-s) -> patch row (2-r, 2-s)
-            const int shift16 = (DGRAD ? ((2 - r) * PW + (2 - s3)) : (r * PW + s3)) * 8;
+            const int shift16 = STEM ? 0 : (DGRAD ? ((2 - r) * PW + (2 - s3)) : (r * PW + s3)) * 8;
             const uint64_t db_tap = RESIDENT ? db_chunk + (uint64_t)(tp * (C::B_TILE >> 4))
                                              : descB0 + (uint64_t)(smemB16 + bs * (C::B_TILE >> 4));
 #pragma unroll
@@ -358,10 +365,10 @@ int map_w(CUtensorMap* m, const void* base, long rows, long cols, int box_rows) 
   return 0;
 }
 
-template <int BN, bool DGRAD, bool RESIDENT>
+template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cudaStream_t s) {
   using C = HCfg<BN, DGRAD, RESIDENT>;
-  const int resident_bytes = RESIDENT ? p.chunks * 9 * C::B_TILE : 0;
+  const int resident_bytes = RESIDENT ? p.chunks * (STEM ? 1 : 9) * C::B_TILE : 0;
   const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
   int a_stages = (int)((227 * 1024 - 1024 - 512 - b_bytes) / PATCH_STRIDE);
   if (a_stages > 6) a_stages = 6;
@@ -371,12 +378,12 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
     fd_set_error("conv_halo: shared memory budget exceeded", __FILE__, __LINE__);
     return -1;
   }
-  FD_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, RESIDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FD_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, RESIDENT, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = h_sms / p.n_tiles * p.n_tiles;
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
   if (grid < p.n_tiles) grid = p.n_tiles;
-  conv_halo_kernel<BN, DGRAD, RESIDENT><<<grid, kThreads, smem, s>>>(a, b, p, resident_bytes, a_stages);
+  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM><<<grid, kThreads, smem, s>>>(a, b, p, resident_bytes, a_stages);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -587,7 +594,186 @@ int map_tile4d(CUtensorMap* m, const void* base, int N, int H, int W, int C, int
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------ stem wgrad
+// dW2[k, a, (b,ch)] = sum_pixels dY[pix, k] * X2[pix + (a, b), ch]   (4x4 stride-1 conv over the s2d input).
+// Per 16x8 spatial tile: one dY tile (M-major, 64 k; rows 64..127 of the M=128 MMA are TMA zero-fill) and four
+// X2 tiles (one per filter row a, each [128 pixels x 64 (b,ch)] through the overlapping-stride map, N-major);
+// four 64-column TMEM accumulators; fp32 vector atomics at the end (split over spatial tiles).
+constexpr int SW_STAGE = 32768 + 4 * 16384;  // 96 KB
+constexpr int SW_STAGES = 2;
+
+struct SWParams {
+  int m_tiles, tiles_h, tiles_w, splits;
+  float* dw2;  // [64][4][64]
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+stem_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_constant__ CUtensorMap mapX, const SWParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SW_STAGES * SW_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + 4;
+  uint64_t* tfull = bars + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const int warp = (int)uniform_u32(threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const uint32_t leader = (lane == 0) ? 1u : 0u;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapDY);
+    tma_prefetch_desc(&mapX);
+    for (int i = 0; i < SW_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(tfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const int split = blockIdx.x;
+  const int mt0 = (int)(((long)P.m_tiles * split) / P.splits);
+  const int mt1 = (int)(((long)P.m_tiles * (split + 1)) / P.splits);
+  if (warp == 0) {
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mt = mt0; mt < mt1; ++mt) {
+      const int n = mt / (P.tiles_h * P.tiles_w);
+      const int rem = mt - n * (P.tiles_h * P.tiles_w);
+      const int th = rem / P.tiles_w, tw = rem - th * P.tiles_w;
+      const int h0 = th * TH, w0 = tw * TW;
+      mbar_wait(&empty[st], ph ^ 1);
+      uint8_t* a = smem + st * SW_STAGE;
+      mbar_arrive_expect_tx_p(&full[st], 32768 + 4 * 16384, leader);
+      tma_load_4d_p(a, &mapDY, &full[st], 0, w0, h0, n, leader);
+      tma_load_4d_p(a + 16384, &mapDY, &full[st], 64, w0, h0, n, leader);  // k >= 64: zero-fill
+#pragma unroll
+      for (int fa = 0; fa < 4; ++fa)
+        tma_load_4d_p(a + 32768 + fa * 16384, &mapX, &full[st], 0, w0, h0 + fa, n, leader);
+      if (++st == SW_STAGES) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+    const uint64_t descA0 = umma_smem_desc(0, 16384, 1024, UMMA_LAYOUT_SW128);
+    const uint64_t descB0 = umma_smem_desc(0, 0, 1024, UMMA_LAYOUT_SW128);
+    const uint32_t smem16 = smem_u32(smem) >> 4;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int mt = mt0; mt < mt1; ++mt) {
+      mbar_wait(&full[st], ph);
+      tc_fence_after();
+      const uint64_t da0 = descA0 + (uint64_t)(smem16 + st * (SW_STAGE >> 4));
+      const uint32_t accflag = (mt > mt0) ? 1u : 0u;
+#pragma unroll
+      for (int fa = 0; fa < 4; ++fa) {
+        const uint64_t db0 = descB0 + (uint64_t)(smem16 + st * (SW_STAGE >> 4) + ((32768 + fa * 16384) >> 4));
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_f16_ss_p(tmem_base + fa * 64, da0 + (uint64_t)(j * 128), db0 + (uint64_t)(j * 128), idesc,
+                        (j > 0) ? 1u : accflag, leader);
+      }
+      umma_commit_p(&empty[st], leader);
+      if (mt == mt1 - 1) umma_commit_p(tfull, leader);
+      if (++st == SW_STAGES) {
+        st = 0;
+        ph ^= 1;
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    if (mt1 > mt0 && quad < 2) {  // only accumulator rows 0..63 carry real output channels
+      mbar_wait(tfull, 0);
+      tc_fence_after();
+      const int krow = quad * 32 + lane;
+#pragma unroll
+      for (int fa = 0; fa < 4; ++fa)
+#pragma unroll
+        for (int c0 = 0; c0 < 64; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + fa * 64 + c0, v);
+          tmem_ld_wait();
+          float* o = P.dw2 + ((long)krow * 4 + fa) * 64 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            atomicAdd(reinterpret_cast<float4*>(o + j),
+                      make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                  __uint_as_float(v[j + 3])));
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// overlapping-stride view of the s2d input X2 [N, HS, WS, 16]: element (n, h, w, e) with e in [0,64) is
+// X2[n, h, w + e/16, e%16]; rows are 128 B long but only 32 B apart.
+int map_s2d_overlap(CUtensorMap* m, const void* base, int N, int HS, int WS) {
+  cuuint64_t dims[4] = {64, (cuuint64_t)(WS - 3), (cuuint64_t)HS, (cuuint64_t)N};
+  cuuint64_t st[3] = {32, (cuuint64_t)WS * 32, (cuuint64_t)HS * WS * 32};
+  cuuint32_t box[4] = {64, TW, TH, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = h_enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, st, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fd_set_error("stem: overlapping-stride tensor map rejected by the driver", __FILE__, (int)r);
+    return -1;
+  }
+  return 0;
+}
+
 }  // namespace
+
+// x2: [N, 115, 115, 16] bf16 (space-to-depth of the padded 224x224x3 image), w2: [64, 256] bf16, y: [N,112,112,64]
+int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int N, int HS, int WS,
+                  cudaStream_t s) {
+  if (h_init()) return -1;
+  const int HO = HS - 3, WO = WS - 3;
+  if (sum) {
+    FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, 64 * sizeof(float), s));
+    FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, 64 * sizeof(float), s));
+  }
+  HParams p{};
+  p.N = N; p.H = HO; p.W = WO; p.Cred = 256; p.Nout = 64; p.chunks = 4;
+  p.tiles_h = (HO + TH - 1) / TH; p.tiles_w = (WO + TW - 1) / TW;
+  p.m_tiles = N * p.tiles_h * p.tiles_w; p.n_tiles = 1;
+  p.wcols = 0; p.out = y; p.sum = sum; p.sumsq = sumsq; p.dbg = 0;
+  CUtensorMap ma, mb;
+  if (map_s2d_overlap(&ma, x2, N, HS, WS)) return -1;
+  if (map_w(&mb, w2, 64, 256, 64)) return -1;
+  return launch_halo<64, false, true, true>(ma, mb, p, s);
+}
+
+int fd_stem_wgrad(const void* dy, const void* x2, float* dw2, int N, int HS, int WS, cudaStream_t s) {
+  if (h_init()) return -1;
+  const int HO = HS - 3, WO = WS - 3;
+  SWParams p{};
+  p.tiles_h = (HO + TH - 1) / TH; p.tiles_w = (WO + TW - 1) / TW;
+  p.m_tiles = N * p.tiles_h * p.tiles_w;
+  p.splits = h_sms < p.m_tiles ? h_sms : p.m_tiles;
+  p.dw2 = dw2;
+  CUtensorMap mdy, mx;
+  if (map_tile4d(&mdy, dy, N, HO, WO, 64, TW, TH)) return -1;
+  if (map_s2d_overlap(&mx, x2, N, HS, WS)) return -1;
+  const int smem = SW_STAGES * SW_STAGE + 1024 + 256;
+  FD_CUDA_CHECK(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  stem_wgrad_kernel<<<p.splits, kThreads, smem, s>>>(mdy, mx, p);
+  FD_LAUNCH_OK();
+  return 0;
+}
 
 int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
                      cudaStream_t s) {

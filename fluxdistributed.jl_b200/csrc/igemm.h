@@ -18,3 +18,6 @@ int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, int N, int H, int 
                      cudaStream_t s);
 int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
                      cudaStream_t s);
+// stem: 7x7/2 conv as a 4x4/1 conv over the space-to-depth input (conv_halo_sm100.cu)
+int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int N, int HS, int WS, cudaStream_t s);
+int fd_stem_wgrad(const void* dy, const void* x2, float* dw2, int N, int HS, int WS, cudaStream_t s);

@@ -473,6 +473,64 @@ normalize_u8_kernel(const uint8_t* __restrict__ in, bf16* __restrict__ out, long
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem helpers: the 7x7/stride-2/pad-3 conv over 3 channels is run as a 4x4/stride-1 conv over the 2x2
+// space-to-depth transform of the padded image (12 real + 4 zero channels = 32 B per pixel), which gives the
+// tensor cores K = 16 taps x 16 channels instead of a 3-channel gather.
+//   X2[n, i, j, (di*2+dj)*3 + c] = xpad[n, 2i+di, 2j+dj, c],  xpad = x zero-padded by 3
+//   W2[k, a, b, (di*2+dj)*3 + c] = w[k, 2a+di, 2b+dj, c]  (zero where 2a+di or 2b+dj == 7)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+s2d_pad_kernel(const bf16* __restrict__ x, bf16* __restrict__ x2, int N, int H, int W, int HS, int WS, int pad) {
+  const long total = (long)N * HS * WS;
+  for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % WS);
+    long r = t / WS;
+    const int i = (int)(r % HS);
+    const int n = (int)(r / HS);
+    float f[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) f[e] = 0.f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+      for (int dj = 0; dj < 2; ++dj) {
+        const int h = 2 * i + di - pad, w = 2 * j + dj - pad;
+        if (h >= 0 && h < H && w >= 0 && w < W) {
+          const bf16* px = x + (((long)n * H + h) * W + w) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) f[(di * 2 + dj) * 3 + c] = __bfloat162float(px[c]);
+        }
+      }
+    stg8(x2 + t * 16, pack8(f));
+    stg8(x2 + t * 16 + 8, pack8(f + 8));
+  }
+}
+
+__global__ void stem_w_s2d_kernel(const bf16* __restrict__ w, bf16* __restrict__ w2, int K) {
+  // w: [K,7,7,3] (KRSC) -> w2: [K,4,4,16]
+  const int total = K * 256;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int e = t & 15, b = (t >> 4) & 3, a = (t >> 6) & 3, k = t >> 8;
+    float v = 0.f;
+    if (e < 12) {
+      const int di = e / 6, dj = (e / 3) & 1, c = e % 3;
+      const int r = 2 * a + di, s = 2 * b + dj;
+      if (r < 7 && s < 7) v = __bfloat162float(w[((k * 7 + r) * 7 + s) * 3 + c]);
+    }
+    w2[t] = __float2bfloat16_rn(v);
+  }
+}
+
+__global__ void stem_dw_from_s2d_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int K) {
+  // dw[k,r,s,c] += dw2[k, r/2, s/2, ((r&1)*2 + (s&1))*3 + c]
+  const int total = K * 147;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int c = t % 3, s = (t / 3) % 7, r = (t / 21) % 7, k = t / 147;
+    dw[t] += dw2[((k * 4 + (r >> 1)) * 4 + (s >> 1)) * 16 + ((r & 1) * 2 + (s & 1)) * 3 + c];
+  }
+}
+
 // fp32 -> bf16 cast of a flat buffer (weights arena -> compute copy)
 __global__ void __launch_bounds__(256) cast_f32_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long n4) {
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
@@ -684,6 +742,24 @@ int fd_bias_add(void* y, const float* bias, int M, int N, cudaStream_t s) {
 }
 int fd_colsum(const void* d, float* out, int M, int N, cudaStream_t s) {
   colsum_kernel<<<(N + 255) / 256, 256, 0, s>>>(reinterpret_cast<const bf16*>(d), out, M, N);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_s2d_pad(const void* x, void* x2, int N, int H, int W, int pad, cudaStream_t s) {
+  const int HS = (H + 2 * pad) / 2, WS = (W + 2 * pad) / 2;
+  s2d_pad_kernel<<<grid_for((long)N * HS * WS, 256, 148 * 16), 256, 0, s>>>(reinterpret_cast<const bf16*>(x),
+                                                                          reinterpret_cast<bf16*>(x2), N, H, W, HS, WS, pad);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s) {
+  stem_w_s2d_kernel<<<(K * 256 + 255) / 256, 256, 0, s>>>(reinterpret_cast<const bf16*>(w), reinterpret_cast<bf16*>(w2), K);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s) {
+  stem_dw_from_s2d_kernel<<<(K * 147 + 255) / 256, 256, 0, s>>>(dw2, dw, K);
   FD_LAUNCH_OK();
   return 0;
 }

@@ -24,3 +24,6 @@ int fd_small_gemm(const void* A, const void* B, float* Cf, void* Cb, int M, int 
                   long sbn, long ldc, cudaStream_t s);
 int fd_bias_add(void* y, const float* bias, int M, int N, cudaStream_t s);
 int fd_colsum(const void* d, float* out, int M, int N, cudaStream_t s);
+int fd_s2d_pad(const void* x, void* x2, int N, int H, int W, int pad, cudaStream_t s);
+int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s);
+int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s);

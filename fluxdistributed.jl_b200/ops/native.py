@@ -93,6 +93,43 @@ def conv3x3_wgrad(dy: torch.Tensor, x: torch.Tensor, out: Optional[torch.Tensor]
     return out
 
 
+def stem_s2d(x: torch.Tensor) -> torch.Tensor:
+    """bf16 NHWC-physical image batch [N,3,H,W] -> space-to-depth tensor X2 [N,(H+6)/2,(W+6)/2,16]."""
+    xh = nhwc(x)
+    n, h, w, c = xh.shape
+    assert c == 3 and h % 2 == 0 and w % 2 == 0
+    x2 = torch.empty(n, (h + 6) // 2, (w + 6) // 2, 16, dtype=BF16, device=x.device)
+    _ext().s2d_pad(xh, x2, 3)
+    return x2
+
+
+def stem_fprop(x2: torch.Tensor, w: torch.Tensor, stats: bool = False):
+    """7x7/2/pad-3 conv, 3->64 channels, as a 4x4/1 tcgen05 conv over the s2d input ``x2``."""
+    wk = krsc(w)
+    w2 = torch.empty(wk.shape[0], 256, dtype=BF16, device=w.device)
+    _ext().stem_w_s2d(wk, w2)
+    n, hs, ws, _ = x2.shape
+    y = torch.empty(n, hs - 3, ws - 3, 64, dtype=BF16, device=x2.device)
+    s = ss = None
+    if stats:
+        s = torch.empty(64, dtype=torch.float32, device=x2.device)
+        ss = torch.empty(64, dtype=torch.float32, device=x2.device)
+    _ext().stem_fprop(x2, w2, y, s, ss)
+    return (from_nhwc(y), s, ss) if stats else from_nhwc(y)
+
+
+def stem_wgrad(dy: torch.Tensor, x2: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Weight gradient of the stem conv as [64,3,7,7] (channels_last) fp32, accumulated into ``out`` if given."""
+    dw2 = torch.zeros(64, 256, dtype=torch.float32, device=dy.device)
+    _ext().stem_wgrad(nhwc(dy), x2, dw2)
+    if out is None:
+        out = torch.zeros(64, 3, 7, 7, dtype=torch.float32, device=dy.device).contiguous(memory_format=torch.channels_last)
+    buf = out.permute(0, 2, 3, 1)
+    assert buf.is_contiguous()
+    _ext().stem_dw_from_s2d(dw2, buf)
+    return out
+
+
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int) -> torch.Tensor:
     """Data gradient.  Stride 1 runs the tcgen05 dgrad directly; stride 2 zero-upsamples ``dy``
     (``dy_up[2i,2j] = dy[i,j]``) and reuses the stride-1 kernel."""
@@ -199,6 +236,13 @@ def _tc_ok(cin: int, cout: int) -> bool:
     return cin % 64 == 0 and cout % 64 == 0
 
 
+def _is_stem(w_shape, stride, pad, x_shape) -> bool:
+    ok = tuple(w_shape) == (64, 3, 7, 7) and stride == 2 and pad == 3
+    if ok and x_shape is not None:
+        ok = x_shape[2] % 16 == 0 and x_shape[3] % 16 == 0 and x_shape[2] >= 32
+    return ok
+
+
 def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
     """Per-shape kernel choice measured by scripts/conv_bench.py (profiles/conv_bench_r1.json): the halo kernel
     wins when the filter slice is small enough to stay resident in shared memory and the image is large
@@ -220,7 +264,13 @@ class _ConvBNAct(torch.autograd.Function):
             y = conv3x3_fprop(x, wl)  # halo-tile kernel: one patch load serves all 9 taps
         elif tc:
             y = conv_fprop(x, wl, stride, pad)
-        else:  # C=3 stem: tensor-core tiling needs C%64==0 (space-to-depth stem is the planned native path)
+        elif _is_stem(w.shape, stride, pad, x.shape):
+            orig_shape = tuple(x.shape)
+            x2 = stem_s2d(x)  # space-to-depth: the 7x7/2 conv becomes a 4x4/1 conv with K = 16 taps x 16 channels
+            y = stem_fprop(x2, wl)
+            x = x2  # saved for the weight gradient instead of the image
+            ctx.orig_shape = orig_shape
+        else:  # other non-64-multiple channel counts fall back to the library
             y = F.conv2d(x, wl, None, stride, pad)
             y = y.contiguous(memory_format=torch.channels_last)
         if training:
@@ -229,14 +279,15 @@ class _ConvBNAct(torch.autograd.Function):
             s = ss = gamma  # unused
         out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
         ctx.save_for_backward(x, wl, y, out if relu else None, mean, rstd, gamma)
-        ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape), k3)
+        stem = (not tc) and _is_stem(w.shape, stride, pad, None)
+        ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape), k3, stem)
         ctx.w_gradbuf, ctx.g_gradbuf, ctx.b_gradbuf = w_gradbuf if isinstance(w_gradbuf, tuple) else (w_gradbuf, None, None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         x, wl, y, out, mean, rstd, gamma = ctx.saved_tensors
-        relu, stride, pad, has_res, tc, w_shape, x_shape, k3 = ctx.cfg
+        relu, stride, pad, has_res, tc, w_shape, x_shape, k3, stem = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
         dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
                                          dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
@@ -248,9 +299,13 @@ class _ConvBNAct(torch.autograd.Function):
                 dx = conv3x3_dgrad(dy, wl)
             elif tc:
                 dx = conv_dgrad(dy, wl, x_shape, stride, pad)
+            elif stem:
+                dx = torch.nn.grad.conv2d_input(ctx.orig_shape, wl, dy, stride, pad)
             else:
                 dx = torch.nn.grad.conv2d_input(x_shape, wl, dy, stride, pad)
-        if k3 and x_shape[2] >= 14:
+        if stem:
+            gw = stem_wgrad(dy, x, out=ctx.w_gradbuf)  # x holds the s2d tensor here
+        elif k3 and x_shape[2] >= 14:
             gw = conv3x3_wgrad(dy, x, out=ctx.w_gradbuf)
         elif tc:
             gw = conv_wgrad(dy, x, w_shape, stride, pad, out=ctx.w_gradbuf)

@@ -135,6 +135,23 @@ def test_halo_wgrad(N, H, W, C, K):
     assert rel_err(dw, ref) < 1e-2
 
 
+@pytest.mark.parametrize("N,HW", [(2, 64), (3, 224), (2, 96)])
+def test_stem_s2d_fprop_wgrad(N, HW):
+    x = cl(torch.randn(N, 3, HW, HW, device="cuda").to(BF))
+    w = cl((torch.randn(64, 3, 7, 7, device="cuda") * 0.1).to(BF))
+    x2 = ops.stem_s2d(x)
+    assert x2.shape == (N, (HW + 6) // 2, (HW + 6) // 2, 16)
+    y, s, ss = ops.stem_fprop(x2, w, stats=True)
+    ref = REF.conv_fprop_ref(x, w, 2, 3)
+    assert y.shape == ref.shape
+    assert rel_err(y, ref) < 1e-2
+    assert rel_err(s, y.float().sum(dim=(0, 2, 3))) < 1e-3
+    dy = cl(torch.randn_like(ref).to(BF))
+    dw = ops.stem_wgrad(dy, x2)
+    rw = REF.conv_wgrad_ref(dy, x, (64, 3, 7, 7), 2, 3)
+    assert rel_err(dw, rw) < 1e-2
+
+
 @pytest.mark.parametrize("C,relu,res", [(64, True, False), (128, True, True), (512, False, False)])
 def test_bn_fwd_bwd(C, relu, res):
     y = cl((torch.randn(6, C, 10, 10, device="cuda") * 2 + 0.5).to(BF))
