@@ -146,12 +146,12 @@ void bn_apply(at::Tensor y, c10::optional<at::Tensor> res, at::Tensor out, at::T
         "bn_apply");
 }
 void bn_bwd(at::Tensor dout, at::Tensor y, c10::optional<at::Tensor> out, at::Tensor mean, at::Tensor rstd,
-            at::Tensor gamma, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy, c10::optional<at::Tensor> dres,
-            bool relu) {
+            at::Tensor gamma, at::Tensor beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy,
+            c10::optional<at::Tensor> dres, bool relu) {
   c10::cuda::CUDAGuard guard(y.device());
   const int C = (int)gamma.numel();
   check(fd_bn_bwd(dout.data_ptr(), y.data_ptr(), optptr(out), mean.data_ptr<float>(), rstd.data_ptr<float>(),
-                  gamma.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr(),
+                  gamma.data_ptr<float>(), beta.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(), dy.data_ptr(),
                   dres.has_value() ? dres->data_ptr() : nullptr, y.numel() / C, C, relu, cur_stream()),
         "bn_bwd");
 }

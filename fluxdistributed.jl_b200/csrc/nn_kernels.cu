@@ -126,38 +126,58 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
   __syncthreads();
   const int C8 = C / 8;
   const long total = M * C8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    float f[8], r[8];
-    unpack8(ldg8(y + i * 8), f);
-    if (res) unpack8(ldg8(res + i * 8), r);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = f[j] * sc[cv * 8 + j] + sh[cv * 8 + j];
-      if (res) v += r[j];
-      if (relu) v = fmaxf(v, 0.f);
-      f[j] = v;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long i1 = i + stride;
+    const bool has1 = i1 < total;
+    V8 y0 = ldg8(y + i * 8), y1, r0, r1;
+    if (has1) y1 = ldg8(y + i1 * 8);
+    if (res) {
+      r0 = ldg8(res + i * 8);
+      if (has1) r1 = ldg8(res + i1 * 8);
     }
-    stg8(out + i * 8, pack8(f));
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const long ii = u ? i1 : i;
+      const int cv = (int)(ii % C8);
+      float f[8], r[8];
+      unpack8(u ? y1 : y0, f);
+      if (res) unpack8(u ? r1 : r0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = f[j] * sc[cv * 8 + j] + sh[cv * 8 + j];
+        if (res) v += r[j];
+        if (relu) v = fmaxf(v, 0.f);
+        f[j] = v;
+      }
+      stg8(out + ii * 8, pack8(f));
+    }
   }
 }
 
 // BN backward pass 1: dgamma[c] = sum dz*xhat, dbeta[c] = sum dz, with dz = dout * (out > 0) if relu
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, long M, int C, int relu) {
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta, long M, int C,
+                     int relu) {
+  // relu mask: from the saved activation `out` when given (residual layers: the pre-activation includes the
+  // skip input), otherwise recomputed from y as (gamma*xhat + beta > 0) — one tensor less to read.
   extern __shared__ float smem[];
   const int C8 = C / 8;
   const int RL = 256 / C8;
   const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
   float acc[2][8];
-  float mu[8], rs[8];
+  float mu[8], rs[8], gsc[8], gsh[8];
+  const bool from_y = relu && (out == nullptr);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     acc[0][j] = acc[1][j] = 0.f;
     mu[j] = mean[cv * 8 + j];
     rs[j] = rstd[cv * 8 + j];
+    gsc[j] = gamma[cv * 8 + j] * rs[j];
+    gsh[j] = beta[cv * 8 + j] - mu[j] * gsc[j];
   }
   if (rl < RL) {
     const long per = (M + gridDim.x - 1) / gridDim.x;
@@ -166,15 +186,22 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, 
     for (; r + RL < r1; r += 2L * RL) {  // two rows (six 16-byte loads) in flight per thread
       const long o0 = r * C + cv * 8, o1 = (r + RL) * C + cv * 8;
       V8 a0 = ldg8(dout + o0), a1 = ldg8(dout + o1), b0 = ldg8(y + o0), b1 = ldg8(y + o1), c0, c1;
-      if (relu) {
+      if (relu && !from_y) {
         c0 = ldg8(out + o0);
         c1 = ldg8(out + o1);
       }
       float d0[8], d1[8], y0[8], y1[8], q0[8], q1[8];
       unpack8(a0, d0); unpack8(a1, d1); unpack8(b0, y0); unpack8(b1, y1);
-      if (relu) {
+      if (relu && !from_y) {
         unpack8(c0, q0);
         unpack8(c1, q1);
+      }
+      if (from_y) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          q0[j] = y0[j] * gsc[j] + gsh[j];
+          q1[j] = y1[j] * gsc[j] + gsh[j];
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -188,11 +215,12 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, 
       float d[8], yy[8], o[8];
       unpack8(ldg8(dout + r * C + cv * 8), d);
       unpack8(ldg8(y + r * C + cv * 8), yy);
-      if (relu) unpack8(ldg8(out + r * C + cv * 8), o);
+      if (relu && !from_y) unpack8(ldg8(out + r * C + cv * 8), o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float dz = d[j];
-        if (relu && !(o[j] > 0.f)) dz = 0.f;
+        const float pre = from_y ? (yy[j] * gsc[j] + gsh[j]) : o[j];
+        if (relu && !(pre > 0.f)) dz = 0.f;
         acc[0][j] += dz * (yy[j] - mu[j]) * rs[j];
         acc[1][j] += dz;
       }
@@ -205,12 +233,15 @@ bn_bwd_reduce_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, 
 __global__ void __launch_bounds__(256)
 bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
-                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, bf16* __restrict__ dy,
-                    bf16* __restrict__ dres, long M, int C, int relu) {
-  extern __shared__ float smem[];  // a[C], b[C], c[C], mean[C]:  dy = a*dz + b*y + c
+                    const float* __restrict__ beta, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                    bf16* __restrict__ dy, bf16* __restrict__ dres, long M, int C, int relu) {
+  extern __shared__ float smem[];  // a[C], b[C], c[C], sc[C], sh[C]:  dy = a*dz + b*y + c ; pre-act = sc*y + sh
   float* ka = smem;
   float* kb = smem + C;
   float* kc = smem + 2 * C;
+  float* ksc = smem + 3 * C;
+  float* ksh = smem + 4 * C;
+  const bool from_y = relu && (out == nullptr);
   const float invM = 1.f / (float)M;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gamma[c], rs = rstd[c], mu = mean[c];
@@ -219,24 +250,43 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
     ka[c] = g * rs;
     kb[c] = -g * rs * rs * dg;
     kc[c] = g * rs * (mu * rs * dg - db);
+    ksc[c] = g * rs;
+    ksh[c] = beta[c] - mu * g * rs;
   }
   __syncthreads();
   const int C8 = C / 8;
   const long total = M * C8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    float d[8], yy[8], o[8];
-    unpack8(ldg8(dout + i * 8), d);
-    unpack8(ldg8(y + i * 8), yy);
-    if (relu) unpack8(ldg8(out + i * 8), o);
-    float dz[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dz[j] = (relu && !(o[j] > 0.f)) ? 0.f : d[j];
-      d[j] = ka[cv * 8 + j] * dz[j] + kb[cv * 8 + j] * yy[j] + kc[cv * 8 + j];
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long i1 = i + stride;
+    const bool has1 = i1 < total;
+    V8 a0 = ldg8(dout + i * 8), b0 = ldg8(y + i * 8), a1, b1, c0, c1;
+    if (has1) {
+      a1 = ldg8(dout + i1 * 8);
+      b1 = ldg8(y + i1 * 8);
     }
-    stg8(dy + i * 8, pack8(d));
-    if (dres) stg8(dres + i * 8, pack8(dz));
+    if (relu && !from_y) {
+      c0 = ldg8(out + i * 8);
+      if (has1) c1 = ldg8(out + i1 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const long ii = u ? i1 : i;
+      const int cv = (int)(ii % C8);
+      float d[8], yy[8], o[8], dz[8];
+      unpack8(u ? a1 : a0, d);
+      unpack8(u ? b1 : b0, yy);
+      if (relu && !from_y) unpack8(u ? c1 : c0, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = from_y ? (yy[j] * ksc[cv * 8 + j] + ksh[cv * 8 + j]) : o[j];
+        dz[j] = (relu && !(pre > 0.f)) ? 0.f : d[j];
+        d[j] = ka[cv * 8 + j] * dz[j] + kb[cv * 8 + j] * yy[j] + kc[cv * 8 + j];
+      }
+      stg8(dy + ii * 8, pack8(d));
+      if (dres) stg8(dres + ii * 8, pack8(dz));
+    }
   }
 }
 
@@ -628,7 +678,7 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
 int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, const float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, cudaStream_t s) {
-  int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
+  int grid = grid_for(M * (C / 8), 256 * 2, 148 * 8);
   bn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res), reinterpret_cast<bf16*>(out), sum, sumsq,
       gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu);
@@ -637,8 +687,8 @@ int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, con
 }
 
 int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
-              const float* gamma, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C, int relu,
-              cudaStream_t s) {
+              const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C,
+              int relu, cudaStream_t s) {
   const int C8 = C / 8;
   const int RL = 256 / C8;
   if (RL == 0) { fd_set_error("bn_bwd: C too large", __FILE__, __LINE__); return -1; }
@@ -647,12 +697,12 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
   int grid = grid_for((M + 2L * RL - 1) / (2L * RL), 1, 148 * 6);
   bn_bwd_reduce_kernel<<<grid, 256, (size_t)RL * C * 2 * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
-      rstd, dgamma, dbeta, M, C, relu);
+      rstd, gamma, beta, dgamma, dbeta, M, C, relu);
   FD_LAUNCH_OK();
-  int grid2 = grid_for(M * C8, 256 * 4, 148 * 8);
-  bn_bwd_apply_kernel<<<grid2, 256, 3 * C * sizeof(float), s>>>(
+  int grid2 = grid_for(M * C8, 256 * 2, 148 * 8);
+  bn_bwd_apply_kernel<<<grid2, 256, 5 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
-      rstd, gamma, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), M, C, relu);
+      rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), M, C, relu);
   FD_LAUNCH_OK();
   return 0;
 }

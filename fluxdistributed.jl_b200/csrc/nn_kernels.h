@@ -7,8 +7,8 @@ int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, con
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, cudaStream_t s);
 int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
-              const float* gamma, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C, int relu,
-              cudaStream_t s);
+              const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C,
+              int relu, cudaStream_t s);
 int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
 int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
                    int stride, int pad, cudaStream_t s);

@@ -183,14 +183,17 @@ def bn_apply(y, s, ss, gamma, beta, eps, residual=None, relu=True, running_mean=
     return from_nhwc(out), mean, rstd
 
 
-def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=None, dbeta=None):
+def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=None, dbeta=None, beta=None):
     yh = nhwc(y)
     c = y.shape[1]
     dy = torch.empty_like(yh)
     dres = torch.empty_like(yh) if want_dres else None
     dgamma = dgamma if dgamma is not None else torch.empty(c, dtype=torch.float32, device=y.device)
     dbeta = dbeta if dbeta is not None else torch.empty(c, dtype=torch.float32, device=y.device)
-    _ext().bn_bwd(nhwc(dout), yh, nhwc(out) if relu else None, mean, rstd, gamma, dgamma, dbeta, dy, dres, relu)
+    # `out=None` with relu: the mask is recomputed from y (valid when there is no residual input)
+    beta = beta if beta is not None else torch.zeros_like(gamma)
+    _ext().bn_bwd(nhwc(dout), yh, nhwc(out) if (relu and out is not None) else None, mean, rstd, gamma, beta, dgamma,
+                  dbeta, dy, dres, relu)
     return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
 
 
@@ -278,7 +281,8 @@ class _ConvBNAct(torch.autograd.Function):
         else:
             s = ss = gamma  # unused
         out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
-        ctx.save_for_backward(x, wl, y, out if relu else None, mean, rstd, gamma)
+        # residual layers need the saved activation for the ReLU mask; plain layers recompute it from y
+        ctx.save_for_backward(x, wl, y, out if (relu and residual is not None) else None, mean, rstd, gamma, beta)
         stem = (not tc) and _is_stem(w.shape, stride, pad, None)
         ctx.cfg = (relu, stride, pad, residual is not None, tc, tuple(w.shape), tuple(x.shape), k3, stem)
         ctx.w_gradbuf, ctx.g_gradbuf, ctx.b_gradbuf = w_gradbuf if isinstance(w_gradbuf, tuple) else (w_gradbuf, None, None)
@@ -286,11 +290,11 @@ class _ConvBNAct(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        x, wl, y, out, mean, rstd, gamma = ctx.saved_tensors
+        x, wl, y, out, mean, rstd, gamma, beta = ctx.saved_tensors
         relu, stride, pad, has_res, tc, w_shape, x_shape, k3, stem = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
         dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
-                                         dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
+                                         dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf, beta=beta)
         if ctx.g_gradbuf is not None:  # landed in the arena: autograd must not accumulate them again
             dgamma = dbeta = None
         dx = None

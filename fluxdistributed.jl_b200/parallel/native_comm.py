@@ -182,7 +182,11 @@ class NativeComm:
         n = a.padded
         mode = self.mode_override
         if mode is None:
-            mode = MODE_ONE_SHOT if (n * 4 <= self.one_shot_max_bytes or self.world == 1) else MODE_TWO_SHOT
+            # measured (profiles/allreduce_update_sweep_x8.jsonl): with NVLS the two-shot kernel wins at every size
+            # (14 us at 64 KB vs 42 us one-shot on 8 GPUs); without multicast one-shot only pays off for tiny
+            # buckets on very small worlds, where its single barrier pair beats reading 1/N from each peer
+            small = n * 4 <= self.one_shot_max_bytes and self.world <= 2 and not mc[0]
+            mode = MODE_ONE_SHOT if (self.world == 1 or small) else MODE_TWO_SHOT
         use_nvls = 1 if (mc[0] and mode == MODE_TWO_SHOT and self.world > 1) else 0
         boundary = _lowp_only_boundary(rep.model, a)
         wout32 = list(w32_ptrs)

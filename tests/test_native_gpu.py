@@ -169,7 +169,7 @@ def test_bn_fwd_bwd(C, relu, res):
     assert rel_err(out, ref) < 1e-2
     assert torch.allclose(rm, 0.1 * mean_ref, atol=1e-3)
     dout = cl(torch.randn_like(ref).to(BF))
-    dy, dg, db, dres = ops.bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=res)
+    dy, dg, db, dres = ops.bn_bwd(dout, y, out if res else None, mean, rstd, gamma, relu, want_dres=res, beta=beta)
     rdy, rdg, rdb, rdz = REF.bn_bwd_ref(dout, y, out, mean_ref, var_ref, gamma, 1e-5, relu)
     assert rel_err(dy, rdy) < 2e-2
     assert rel_err(dg, rdg) < 1e-2 and rel_err(db, rdb) < 1e-2
