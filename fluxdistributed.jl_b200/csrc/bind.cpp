@@ -284,6 +284,28 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_stem_wgrad(dy.data_ptr(), x2.data_ptr(), dw2.data_ptr<float>(), (int)x2.size(0), (int)x2.size(1), (int)x2.size(2),
                         cur_stream()), "stem_wgrad");
   });
+  m.def("bn_ws_bytes", [](int C) { return (int64_t)fd_bn_ws_bytes(C); });
+  m.def("bn_fwd_fused", [](at::Tensor y, c10::optional<at::Tensor> res, at::Tensor out, at::Tensor gamma, at::Tensor beta,
+                           c10::optional<at::Tensor> run_mean, c10::optional<at::Tensor> run_var, at::Tensor save_mean,
+                           at::Tensor save_rstd, at::Tensor ws, double eps, double momentum, bool relu) {
+    c10::cuda::CUDAGuard guard(y.device());
+    const int C = (int)gamma.numel();
+    TORCH_CHECK((size_t)ws.numel() * ws.element_size() >= fd_bn_ws_bytes(C), "bn workspace too small");
+    check(fd_bn_fwd_fused(y.data_ptr(), optptr(res), out.data_ptr(), gamma.data_ptr<float>(), beta.data_ptr<float>(),
+                          optf(run_mean), optf(run_var), save_mean.data_ptr<float>(), save_rstd.data_ptr<float>(),
+                          ws.data_ptr(), y.numel() / C, C, (float)eps, (float)momentum, relu, cur_stream()), "bn_fwd_fused");
+  });
+  m.def("bn_bwd_fused", [](at::Tensor dout, at::Tensor y, c10::optional<at::Tensor> out, at::Tensor mean, at::Tensor rstd,
+                           at::Tensor gamma, at::Tensor beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy,
+                           c10::optional<at::Tensor> dres, at::Tensor ws, bool relu) {
+    c10::cuda::CUDAGuard guard(y.device());
+    const int C = (int)gamma.numel();
+    TORCH_CHECK((size_t)ws.numel() * ws.element_size() >= fd_bn_ws_bytes(C), "bn workspace too small");
+    check(fd_bn_bwd_fused(dout.data_ptr(), y.data_ptr(), optptr(out), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                          gamma.data_ptr<float>(), beta.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                          dy.data_ptr(), dres.has_value() ? dres->data_ptr() : nullptr, ws.data_ptr(), y.numel() / C, C, relu,
+                          cur_stream()), "bn_bwd_fused");
+  });
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd", &bn_bwd);

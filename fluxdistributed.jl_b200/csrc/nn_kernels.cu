@@ -291,6 +291,272 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Single-launch BatchNorm forward / backward.  Most ResNet layers have small activations (5-40 MB) for which
+// the 2-kernel + 2-memset formulation is launch/latency-bound (scripts/bn_bench.py: 10-35 us fixed cost per
+// layer).  These kernels do both passes in one launch: phase 1 block-partial reductions added atomically into a
+// per-channel accumulator -> grid barrier -> every CTA derives the per-channel coefficients -> phase 2 applies
+// them (the second read of a small tensor is an L2 hit).  The accumulator is double-buffered by launch parity:
+// a launch adds into buffer (gen & 1) and clears the other one for the next launch, so no memset is needed.
+// All CTAs are co-resident (grid bounded by the occupancy query).
+// ---------------------------------------------------------------------------------------------
+struct GridSync {
+  unsigned* counter;  // arrivals of this launch
+  unsigned* gen;      // generation, bumped once per launch by the last arriver
+};
+
+FD_DEVINL void grid_barrier(const GridSync& g, unsigned gen0) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(g.counter, 1u);
+    if (prev == gridDim.x - 1) {
+      *g.counter = 0;
+      __threadfence();
+      atomicAdd(g.gen, 1u);
+    } else {
+      while (*reinterpret_cast<volatile unsigned*>(g.gen) == gen0) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+FD_DEVINL void block_accumulate2(float (*acc)[8], int C8, int cv, int rl, int RL, float* smem, float* accum) {
+  // smem [RL][C][2] -> atomicAdd into accum[2][C]
+  const int Cc = C8 * 8;
+  if (rl < RL) {
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) smem[(rl * Cc + cv * 8 + j) * 2 + q] = acc[q][j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cc * 2; c += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < RL; ++r) s += smem[r * Cc * 2 + c];
+    atomicAdd(accum + (long)(c & 1) * Cc + (c >> 1), s);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+bn_fwd_fused_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* __restrict__ out,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ run_mean,
+                    float* __restrict__ run_var, float* __restrict__ save_mean, float* __restrict__ save_rstd,
+                    float* __restrict__ accbuf, GridSync gs, long M, int C, float eps, float momentum, int relu) {
+  extern __shared__ float smem[];
+  __shared__ unsigned s_gen0;
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
+  if (threadIdx.x == 0) s_gen0 = *reinterpret_cast<volatile unsigned*>(gs.gen);
+  float acc[2][8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[0][j] = acc[1][j] = 0.f;
+  if (rl < RL) {
+    const long per = (M + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
+    long r = r0 + rl;
+    for (; r + 3L * RL < r1; r += 4L * RL) {
+      V8 v0 = ldg8(y + r * C + cv * 8), v1 = ldg8(y + (r + RL) * C + cv * 8), v2 = ldg8(y + (r + 2L * RL) * C + cv * 8),
+         v3 = ldg8(y + (r + 3L * RL) * C + cv * 8);
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(v0, f0); unpack8(v1, f1); unpack8(v2, f2); unpack8(v3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+        acc[1][j] += (f0[j] * f0[j] + f1[j] * f1[j]) + (f2[j] * f2[j] + f3[j] * f3[j]);
+      }
+    }
+    for (; r < r1; r += RL) {
+      float f[8];
+      unpack8(ldg8(y + r * C + cv * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] += f[j];
+        acc[1][j] += f[j] * f[j];
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned gen0 = s_gen0;
+  float* accum = accbuf + (size_t)(gen0 & 1) * 2 * C;
+  float* other = accbuf + (size_t)((gen0 & 1) ^ 1) * 2 * C;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+  block_accumulate2(acc, C8, cv, rl, RL, smem, accum);
+  grid_barrier(gs, gen0);
+  float* sc = smem;
+  float* sh = smem + C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float mean = __ldcg(accum + c) * invM;
+    const float var = fmaxf(__ldcg(accum + C + c) * invM - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma[c];
+    sc[c] = g * rstd;
+    sh[c] = beta[c] - mean * g * rstd;
+    if (blockIdx.x == 0) {
+      if (save_mean) save_mean[c] = mean;
+      if (save_rstd) save_rstd[c] = rstd;
+      if (run_mean) {
+        const float unbiased = var * ((float)M / fmaxf((float)M - 1.f, 1.f));
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long i1 = i + stride;
+    const bool has1 = i1 < total;
+    V8 y0 = ldg8(y + i * 8), y1, q0, q1;
+    if (has1) y1 = ldg8(y + i1 * 8);
+    if (res) {
+      q0 = ldg8(res + i * 8);
+      if (has1) q1 = ldg8(res + i1 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const long ii = u ? i1 : i;
+      const int ch = (int)(ii % C8);
+      float f[8], r[8];
+      unpack8(u ? y1 : y0, f);
+      if (res) unpack8(u ? q1 : q0, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = f[j] * sc[ch * 8 + j] + sh[ch * 8 + j];
+        if (res) v += r[j];
+        if (relu) v = fmaxf(v, 0.f);
+        f[j] = v;
+      }
+      stg8(out + ii * 8, pack8(f));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                    bf16* __restrict__ dy, bf16* __restrict__ dres, float* __restrict__ accbuf, GridSync gs, long M, int C,
+                    int relu) {
+  extern __shared__ float smem[];
+  __shared__ unsigned s_gen0;
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const bool from_y = relu && (out == nullptr);
+  if (threadIdx.x == 0) s_gen0 = *reinterpret_cast<volatile unsigned*>(gs.gen);
+  float acc[2][8];
+  float mu[8], rs[8], gsc[8], gsh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = 0.f;
+    mu[j] = mean[cv * 8 + j];
+    rs[j] = rstd[cv * 8 + j];
+    gsc[j] = gamma[cv * 8 + j] * rs[j];
+    gsh[j] = beta[cv * 8 + j] - mu[j] * gsc[j];
+  }
+  if (rl < RL) {
+    const long per = (M + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
+    for (long r = r0 + rl; r < r1; r += 2L * RL) {
+      const bool has1 = r + RL < r1;
+      const long o0 = r * C + cv * 8, o1 = (r + RL) * C + cv * 8;
+      V8 a0 = ldg8(dout + o0), b0 = ldg8(y + o0), a1, b1, c0, c1;
+      if (has1) {
+        a1 = ldg8(dout + o1);
+        b1 = ldg8(y + o1);
+      }
+      if (relu && !from_y) {
+        c0 = ldg8(out + o0);
+        if (has1) c1 = ldg8(out + o1);
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u == 1 && !has1) break;
+        float d[8], yy[8], o[8];
+        unpack8(u ? a1 : a0, d);
+        unpack8(u ? b1 : b0, yy);
+        if (relu && !from_y) unpack8(u ? c1 : c0, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = from_y ? (yy[j] * gsc[j] + gsh[j]) : o[j];
+          const float dz = (relu && !(pre > 0.f)) ? 0.f : d[j];
+          acc[0][j] += dz * (yy[j] - mu[j]) * rs[j];
+          acc[1][j] += dz;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned gen0 = s_gen0;
+  float* accum = accbuf + (size_t)(gen0 & 1) * 2 * C;
+  float* other = accbuf + (size_t)((gen0 & 1) ^ 1) * 2 * C;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+  block_accumulate2(acc, C8, cv, rl, RL, smem, accum);
+  grid_barrier(gs, gen0);
+  float* ka = smem;
+  float* kb = smem + C;
+  float* kc = smem + 2 * C;
+  float* ksc = smem + 3 * C;
+  float* ksh = smem + 4 * C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float dg = __ldcg(accum + c), db = __ldcg(accum + C + c);
+    if (blockIdx.x == 0) {
+      dgamma[c] = dg;
+      dbeta[c] = db;
+    }
+    const float g = gamma[c], r_ = rstd[c], m_ = mean[c];
+    ka[c] = g * r_;
+    kb[c] = -g * r_ * r_ * dg * invM;
+    kc[c] = g * r_ * (m_ * r_ * dg * invM - db * invM);
+    ksc[c] = g * r_;
+    ksh[c] = beta[c] - m_ * g * r_;
+  }
+  __syncthreads();
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
+    const long i1 = i + stride;
+    const bool has1 = i1 < total;
+    V8 a0 = ldg8(dout + i * 8), b0 = ldg8(y + i * 8), a1, b1, c0, c1;
+    if (has1) {
+      a1 = ldg8(dout + i1 * 8);
+      b1 = ldg8(y + i1 * 8);
+    }
+    if (relu && !from_y) {
+      c0 = ldg8(out + i * 8);
+      if (has1) c1 = ldg8(out + i1 * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !has1) break;
+      const long ii = u ? i1 : i;
+      const int ch = (int)(ii % C8);
+      float d[8], yy[8], o[8], dz[8];
+      unpack8(u ? a1 : a0, d);
+      unpack8(u ? b1 : b0, yy);
+      if (relu && !from_y) unpack8(u ? c1 : c0, o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pre = from_y ? (yy[j] * ksc[ch * 8 + j] + ksh[ch * 8 + j]) : o[j];
+        dz[j] = (relu && !(pre > 0.f)) ? 0.f : d[j];
+        d[j] = ka[ch * 8 + j] * dz[j] + kb[ch * 8 + j] * yy[j] + kc[ch * 8 + j];
+      }
+      stg8(dy + ii * 8, pack8(d));
+      if (dres) stg8(dres + ii * 8, pack8(dz));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Max-pool (k x k, stride, pad) NHWC, 8 channels per thread; backward recomputes the arg-max
 // (first maximum in scan order, matching PyTorch) instead of storing indices.
 // ---------------------------------------------------------------------------------------------
@@ -810,6 +1076,64 @@ int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s) {
 }
 int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s) {
   stem_dw_from_s2d_kernel<<<(K * 147 + 255) / 256, 256, 0, s>>>(dw2, dw, K);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+// ---- single-launch BN (grid-barrier kernels).  `ws` is a per-layer workspace: [counter, gen, pad, pad] (uint)
+// followed by two [2][C] float accumulators (double-buffered by launch parity).
+static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem);
+  if (per_sm < 1) return 0;
+  if (per_sm > 2) per_sm = 2;
+  long want = (M * (C / 8) + 1023) / 1024;
+  long cap = (long)sms * per_sm;
+  if (want > cap) want = cap;
+  if (want < 1) want = 1;
+  return (int)want;
+}
+
+int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
+                    float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,
+                    float momentum, int relu, cudaStream_t s) {
+  const int C8 = C / 8;
+  const int RL = C8 ? 256 / C8 : 0;
+  if (C % 8 || RL == 0) { fd_set_error("bn_fwd_fused: unsupported C", __FILE__, __LINE__); return -1; }
+  size_t smem = (size_t)RL * C * 2 * sizeof(float);
+  if (smem < (size_t)2 * C * sizeof(float)) smem = 2 * C * sizeof(float);
+  const int grid = bn_fused_grid((const void*)bn_fwd_fused_kernel, smem, M, C);
+  if (grid < 1) { fd_set_error("bn_fwd_fused: occupancy query failed", __FILE__, __LINE__); return -1; }
+  GridSync gs{reinterpret_cast<unsigned*>(ws), reinterpret_cast<unsigned*>(ws) + 1};
+  float* accbuf = reinterpret_cast<float*>(ws) + 4;
+  bn_fwd_fused_kernel<<<grid, 256, smem, s>>>(reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res),
+                                              reinterpret_cast<bf16*>(out), gamma, beta, run_mean, run_var, save_mean,
+                                              save_rstd, accbuf, gs, M, C, eps, momentum, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, void* ws,
+                    long M, int C, int relu, cudaStream_t s) {
+  const int C8 = C / 8;
+  const int RL = C8 ? 256 / C8 : 0;
+  if (C % 8 || RL == 0) { fd_set_error("bn_bwd_fused: unsupported C", __FILE__, __LINE__); return -1; }
+  size_t smem = (size_t)RL * C * 2 * sizeof(float);
+  if (smem < (size_t)5 * C * sizeof(float)) smem = 5 * C * sizeof(float);
+  const int grid = bn_fused_grid((const void*)bn_bwd_fused_kernel, smem, M, C);
+  if (grid < 1) { fd_set_error("bn_bwd_fused: occupancy query failed", __FILE__, __LINE__); return -1; }
+  GridSync gs{reinterpret_cast<unsigned*>(ws), reinterpret_cast<unsigned*>(ws) + 1};
+  float* accbuf = reinterpret_cast<float*>(ws) + 4;
+  bn_bwd_fused_kernel<<<grid, 256, smem, s>>>(
+      reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
+      rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), accbuf, gs, M, C, relu);
   FD_LAUNCH_OK();
   return 0;
 }

@@ -27,3 +27,12 @@ int fd_colsum(const void* d, float* out, int M, int N, cudaStream_t s);
 int fd_s2d_pad(const void* x, void* x2, int N, int H, int W, int pad, cudaStream_t s);
 int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s);
 int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s);
+#define FD_BN_MAX_GRID 296
+// workspace bytes for the single-launch BN kernels with at most `C` channels
+inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)4 * C * sizeof(float); }
+int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
+                    float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,
+                    float momentum, int relu, cudaStream_t s);
+int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
+                    const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, void* ws,
+                    long M, int C, int relu, cudaStream_t s);

@@ -91,13 +91,17 @@ class ConvBN(nn.Module):
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
         if _use_native(x):
             from ..ops import conv_bn_act
+            from ..ops.native import bn_workspace
 
+            ws = self.__dict__.get("_bn_ws")
+            if ws is None or ws.device != x.device:
+                ws = self.__dict__["_bn_ws"] = bn_workspace(self.cout, x.device)
             return conv_bn_act(x, self.conv.weight, self.bn.weight, self.bn.bias, self.bn.running_mean,
                                self.bn.running_var, residual, self.relu, self.stride, self.padding,
                                self.bn.eps, self.bn.momentum, self.training,
                                getattr(self.conv.weight, "_lowp", None),
                                (getattr(self.conv.weight, "_gradbuf", None), getattr(self.bn.weight, "_gradbuf", None),
-                                getattr(self.bn.bias, "_gradbuf", None)))
+                                getattr(self.bn.bias, "_gradbuf", None)), ws)
         w = self.conv.weight
         if x.dtype != w.dtype:
             w = w.to(x.dtype)

@@ -197,6 +197,38 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
     return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
 
 
+BN_FUSED = True  # single-launch grid-barrier BN kernels (disabled when replicas share one physical GPU)
+
+
+def bn_workspace(c: int, device) -> torch.Tensor:
+    """Zero-initialised workspace (counters + block partials + coefficients) for the single-launch BN kernels."""
+    return torch.zeros((_ext().bn_ws_bytes(c) + 3) // 4, dtype=torch.int32, device=device)
+
+
+def bn_fwd_fused(y, gamma, beta, eps, ws, residual=None, relu=True, running_mean=None, running_var=None, momentum=0.1):
+    """Training-mode BN (+residual, +ReLU) in ONE launch: statistics, running-stat update and apply."""
+    yh = nhwc(y)
+    out = torch.empty_like(yh)
+    c = y.shape[1]
+    mean = torch.empty(c, dtype=torch.float32, device=y.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_fwd_fused(yh, None if residual is None else nhwc(residual), out, gamma, beta, running_mean, running_var,
+                        mean, rstd, ws, eps, momentum, relu)
+    return from_nhwc(out), mean, rstd
+
+
+def bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ws, relu=True, want_dres=False, dgamma=None, dbeta=None):
+    yh = nhwc(y)
+    c = y.shape[1]
+    dy = torch.empty_like(yh)
+    dres = torch.empty_like(yh) if want_dres else None
+    dgamma = dgamma if dgamma is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    dbeta = dbeta if dbeta is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_bwd_fused(nhwc(dout), yh, nhwc(out) if (relu and out is not None) else None, mean, rstd, gamma, beta,
+                        dgamma, dbeta, dy, dres, ws, relu)
+    return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
+
+
 def normalize_u8(x_u8: torch.Tensor, cpad: int = 3, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
     """uint8 NHWC [N,H,W,3] -> bf16 logical NCHW (channels_last) with ``cpad`` channels."""
     n, h, w, _ = x_u8.shape
@@ -256,7 +288,7 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                w_gradbuf):
+                w_gradbuf, bn_ws=None):
         wl = w_lowp if w_lowp is not None else w.detach().to(BF16)
         if not wl.permute(0, 2, 3, 1).is_contiguous():
             wl = wl.contiguous(memory_format=torch.channels_last)
@@ -276,11 +308,16 @@ class _ConvBNAct(torch.autograd.Function):
         else:  # other non-64-multiple channel counts fall back to the library
             y = F.conv2d(x, wl, None, stride, pad)
             y = y.contiguous(memory_format=torch.channels_last)
-        if training:
-            s, ss = bn_stats(y)
+        fused_bn = training and BN_FUSED and bn_ws is not None
+        if fused_bn:
+            out, mean, rstd = bn_fwd_fused(y, gamma, beta, eps, bn_ws, residual, relu, rm, rv, momentum)
         else:
-            s = ss = gamma  # unused
-        out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
+            if training:
+                s, ss = bn_stats(y)
+            else:
+                s = ss = gamma  # unused
+            out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
+        ctx.bn_ws = bn_ws if fused_bn else None
         # residual layers need the saved activation for the ReLU mask; plain layers recompute it from y
         ctx.save_for_backward(x, wl, y, out if (relu and residual is not None) else None, mean, rstd, gamma, beta)
         stem = (not tc) and _is_stem(w.shape, stride, pad, None)
@@ -293,8 +330,12 @@ class _ConvBNAct(torch.autograd.Function):
         x, wl, y, out, mean, rstd, gamma, beta = ctx.saved_tensors
         relu, stride, pad, has_res, tc, w_shape, x_shape, k3, stem = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
-        dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
-                                         dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf, beta=beta)
+        if ctx.bn_ws is not None:
+            dy, dgamma, dbeta, dres = bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ctx.bn_ws, relu,
+                                                   want_dres=has_res, dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
+        else:
+            dy, dgamma, dbeta, dres = bn_bwd(dout, y, out, mean, rstd, gamma, relu, want_dres=has_res,
+                                             dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf, beta=beta)
         if ctx.g_gradbuf is not None:  # landed in the arena: autograd must not accumulate them again
             dgamma = dbeta = None
         dx = None
@@ -321,13 +362,13 @@ class _ConvBNAct(torch.autograd.Function):
         # when the gradient already landed in the arena, autograd must not add it a second time
         dw = None if ctx.w_gradbuf is not None else gw
         return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
-                None, None)
+                None, None, None)
 
 
 def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
-                w_gradbuf=None):
+                w_gradbuf=None, bn_ws=None):
     return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                            w_gradbuf)
+                            w_gradbuf, bn_ws)
 
 
 # --------------------------------------------------------------------------- autograd: max-pool, GAP + FC

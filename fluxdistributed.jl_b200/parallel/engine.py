@@ -29,7 +29,7 @@ class GraphedStep:
 
     def __init__(self, rep: FusedReplica, loss: Callable, x_shape: Sequence[int], x_dtype: torch.dtype,
                  y_shape: Sequence[int], y_dtype: torch.dtype, transform: Optional[Callable] = None,
-                 warmup: int = 3, graph: bool = True):
+                 warmup: int = 3, graph: bool = True, capture_error_mode: str = "global"):
         self.rep, self.loss, self.transform = rep, loss, transform
         tdev = rep.dev.torch_device
         with device_ctx(rep.dev):
@@ -39,6 +39,7 @@ class GraphedStep:
         self.graph = None
         self.use_graph = graph and rep.dev.is_cuda
         self.warmup = warmup
+        self.capture_error_mode = capture_error_mode  # "thread_local" when several replica threads capture at once
         self.launches_per_step = 0
         self._captured = False
 
@@ -66,7 +67,7 @@ class GraphedStep:
             torch.cuda.synchronize(rep.dev.torch_device)
             n0 = ops.extension().launch_count() if ops.native_available() else 0
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
                 self._body()
             self.launches_per_step = (ops.extension().launch_count() - n0) if ops.native_available() else 0
             self._captured = True
@@ -160,3 +161,32 @@ class Trainer:
     def finish(self):
         self.group.sync_to_modules()
         return self.model
+
+
+def graphed_replica_step(rep: FusedReplica, x: torch.Tensor, y: torch.Tensor, loss: Callable) -> torch.Tensor:
+    """Task mode (one thread per GPU in one process): run ``rep``'s step through a per-replica CUDA graph keyed by
+    the batch signature.  The first call performs the eager warm-up steps (real training steps, all replicas take
+    part in their barriers) and captures with thread-local capture mode; later calls only copy the batch into the
+    static buffers and replay."""
+    key = (tuple(x.shape), x.dtype, tuple(y.shape), y.dtype)
+    cache = rep.__dict__.setdefault("_graphs", {})
+    gs = cache.get(key)
+    if gs is None:
+        lowp = rep.arena.w16.dtype if rep.arena.w16 is not None else torch.float32
+        if x.dtype == torch.uint8:
+            from .. import ops
+
+            transform = (lambda t: ops.normalize_u8(t, 3))
+        elif x.dim() == 4 and rep.dev.is_cuda:
+            transform = (lambda t: t.to(lowp).contiguous(memory_format=torch.channels_last))
+        else:
+            transform = None
+        gs = GraphedStep(rep, loss, x.shape, x.dtype, y.shape, y.dtype, transform, warmup=2,
+                         capture_error_mode="thread_local")
+        with device_ctx(rep.dev):
+            gs.x.copy_(x)
+            gs.y.copy_(y)
+        gs.capture()
+        cache[key] = gs
+    with device_ctx(rep.dev):
+        return gs(x, y)

@@ -260,12 +260,18 @@ class FusedGroup:
         self.replicas = list(replicas)
         self.comm = comm
         self.loss = loss
+        # task mode replays one CUDA graph per replica and step when the native kernel path is active
+        self.use_graphs = getattr(comm, "name", "") == "native" and all(r.dev.is_cuda for r in self.replicas) \
+            and len({r.dev.cuda_index for r in self.replicas}) == len(self.replicas)
         for r in self.replicas:
             r.group = self
         # replicas that share a physical GPU must run on distinct streams, otherwise the device-side
         # barrier of the fused kernel would wait for a kernel queued behind it on the same stream
         cu = [r.dev.cuda_index for r in self.replicas if r.dev.is_cuda]
         if len(cu) != len(set(cu)):
+            from ..ops import native as _native
+
+            _native.BN_FUSED = False  # grid-barrier kernels of co-located replicas could starve each other
             for r in self.replicas:
                 with device_ctx(r.dev):
                     r.stream = torch.cuda.Stream(device=r.dev.torch_device)

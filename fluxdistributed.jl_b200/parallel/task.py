@@ -276,8 +276,14 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
 
             if setup.engine is not None:
                 # fused path: fwd+bwd per replica, then ONE fused reduce+update kernel per replica
-                futs = [pool.submit(setup.engine.replicas[i].step, mb[0], mb[1], loss)
-                        for i, mb in enumerate(mbs)]
+                if getattr(setup.engine, "use_graphs", False):
+                    from .engine import graphed_replica_step
+
+                    futs = [pool.submit(graphed_replica_step, setup.engine.replicas[i], mb[0], mb[1], loss)
+                            for i, mb in enumerate(mbs)]
+                else:
+                    futs = [pool.submit(setup.engine.replicas[i].step, mb[0], mb[1], loss)
+                            for i, mb in enumerate(mbs)]
                 losses = [f.result() for f in futs]
                 info = {"loss": losses[0]}
             else:

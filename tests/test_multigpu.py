@@ -123,3 +123,24 @@ def test_process_mode_symmetric_memory(nvls, mode):
         for a, b, c in zip(res[r][1], res[0][1], ref.parameters()):
             assert torch.equal(a, b)
             assert torch.allclose(a, c, rtol=1e-3, atol=2e-4)
+
+
+def test_task_mode_train_resnet_graphs():
+    """README recipe on real GPUs (task-based parallelism): prepare_training -> train with the fused engine;
+    every replica thread replays its own CUDA graph; replicas end bit-identical."""
+    from fluxdist.data import SyntheticKey
+
+    n = min(torch.cuda.device_count(), 4)
+    torch.manual_seed(0)
+    model = fd.ResNet18(10)
+    key = SyntheticKey(4000, nclasses=10, shape=(3, 64, 64))
+    opt = fd.Momentum(0.01, 0.9)
+    setup, buffer = fd.prepare_training(model, key, fd.cuda_devices(n), opt, 8, cycle=6, buffersize=2, engine="fused",
+                                        onehot=False, loss=fd.logitcrossentropy)
+    assert setup.engine.use_graphs
+    losses = []
+    out = fd.train(fd.logitcrossentropy, setup, buffer, opt, on_step=lambda j, info: losses.append(float(info["loss"])))
+    assert len(out) == n and len(losses) == 6 and all(l == l for l in losses)
+    for a, b in zip(out[0][1].parameters(), out[-1][1].parameters()):
+        assert torch.equal(a, b)
+    assert any(hasattr(r, "_graphs") for r in setup.engine.replicas)

@@ -177,6 +177,31 @@ def test_bn_fwd_bwd(C, relu, res):
         assert rel_err(dres, rdz) < 1e-2
 
 
+@pytest.mark.parametrize("C,hw,relu,res", [(64, 20, True, False), (128, 14, True, True), (512, 7, False, False), (256, 28, True, True)])
+def test_bn_single_launch_kernels(C, hw, relu, res):
+    from fluxdist.ops import native as N
+
+    y = cl((torch.randn(12, C, hw, hw, device="cuda") * 2 + 0.5).to(BF))
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda")
+    residual = cl(torch.randn_like(y.float()).to(BF)) if res else None
+    ws = N.bn_workspace(C, y.device)
+    mean_ref, var_ref = REF.bn_stats_ref(y)
+    for _ in range(2):  # the workspace (counter / generation flag) must be reusable across launches
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        out, mean, rstd = N.bn_fwd_fused(y, gamma, beta, 1e-5, ws, residual, relu, rm, rv, 0.1)
+        ref = REF.bn_apply_ref(y, mean_ref, var_ref, gamma, beta, 1e-5, residual, relu)
+        assert rel_err(out, ref) < 1e-2
+        assert torch.allclose(mean, mean_ref, atol=2e-3) and torch.allclose(rm, 0.1 * mean_ref, atol=1e-3)
+        dout = cl(torch.randn_like(ref).to(BF))
+        dy, dg, db, dres = N.bn_bwd_fused(dout, y, out if res else None, mean, rstd, gamma, beta, ws, relu, want_dres=res)
+        rdy, rdg, rdb, rdz = REF.bn_bwd_ref(dout, y, out, mean_ref, var_ref, gamma, 1e-5, relu)
+        assert rel_err(dy, rdy) < 2e-2
+        assert rel_err(dg, rdg) < 1e-2 and rel_err(db, rdb) < 1e-2
+        if res:
+            assert rel_err(dres, rdz) < 1e-2
+
+
 def test_maxpool_fwd_bwd():
     x = cl(F.relu(torch.randn(3, 64, 17, 17, device="cuda")).to(BF)).requires_grad_(True)
     out = ops.maxpool2d(x, 3, 2, 1)
@@ -268,6 +293,23 @@ def test_resnet18_native_vs_torch():
     g2 = m2.layer4[1].conv2.conv.weight.grad
     assert rel_err(g1, g2) < 0.3  # bf16 activations + batch-8 BN statistics vs fp32 reference
     assert rel_err(m.head.fc.weight.grad, m2.head.fc.weight.grad) < 0.1
+
+
+def test_resnet50_native_smoke():
+    torch.manual_seed(0)
+    m = cl_model(fd.ResNet50(100)).cuda()
+    x = cl(torch.randn(8, 3, 64, 64, device="cuda"))
+    y = torch.randint(0, 100, (8,), device="cuda")
+    fd.nn.set_backend("native")
+    try:
+        n0 = ops.extension().launch_count()
+        l1 = fd.logitcrossentropy(m(x.to(BF)), y)
+        l1.backward()
+        assert ops.extension().launch_count() - n0 > 300
+    finally:
+        fd.nn.set_backend("auto")
+    assert l1.item() == l1.item() and abs(l1.item() - 4.6) < 1.5
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
 
 
 def cl_model(m):
