@@ -243,6 +243,16 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readonly("grid", &FusedPlan::grid);
   m.def("gather_shards", &gather_shards);
   m.def("gemm_nt", &gemm_nt);
+  m.def("gemm_nn", [](at::Tensor A, at::Tensor B, at::Tensor D) {  // D[M,N] = A[M,K] B[K,N]
+    c10::cuda::CUDAGuard guard(A.device());
+    check(fd_gemm_nn(A.data_ptr(), B.data_ptr(), D.data_ptr(), (int)A.size(0), (int)B.size(1), (int)A.size(1),
+                     D.scalar_type() == at::kFloat, cur_stream()), "gemm_nn");
+  });
+  m.def("gemm_tn", [](at::Tensor A, at::Tensor B, at::Tensor D) {  // D[M,N] = A[K,M]^T B[K,N]
+    c10::cuda::CUDAGuard guard(A.device());
+    check(fd_gemm_tn(A.data_ptr(), B.data_ptr(), D.data_ptr(), (int)A.size(1), (int)B.size(1), (int)A.size(0),
+                     D.scalar_type() == at::kFloat, cur_stream()), "gemm_tn");
+  });
   m.def("conv_fprop", &conv_fprop);
   m.def("conv_dgrad", &conv_dgrad);
   m.def("conv_wgrad", &conv_wgrad);

@@ -32,7 +32,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per k-block = one 128B swizzle row
 constexpr int kThreads = 192;
 
-enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_WGRAD = 3 };
+enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_WGRAD = 3, MODE_GEMM_NN = 4, MODE_GEMM_TN = 5 };
 
 struct KParams {
   int mode;
@@ -145,6 +145,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           if (MODE == MODE_GEMM) {
             tma_load_2d_p(a, &mapA, &full[stage], kb * BK, m0, leader);
             tma_load_2d_p(b, &mapB, &full[stage], kb * BK, n0, leader);
+          } else if (MODE == MODE_GEMM_NN) {  // A[M,K] K-major, B[K,N] N-major
+            tma_load_2d_p(a, &mapA, &full[stage], kb * BK, m0, leader);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_p(b + j * (BK * 128), &mapB, &full[stage], n0 + j * 64, kb * BK, leader);
+          } else if (MODE == MODE_GEMM_TN) {  // A[K,M] M-major, B[K,N] N-major
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_p(a + j * (BK * 128), &mapA, &full[stage], m0 + j * 64, kb * BK, leader);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_p(b + j * (BK * 128), &mapB, &full[stage], n0 + j * 64, kb * BK, leader);
           } else if (MODE == MODE_FPROP) {
             const int tp = kb / P.C_chunks, cc = kb - tp * P.C_chunks;
             const int r = tp / P.S, s = tp - r * P.S;
@@ -181,8 +193,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // ===================================================== MMA issuer
-    constexpr bool A_MN = (MODE == MODE_WGRAD);
-    constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_WGRAD);
+    constexpr bool A_MN = (MODE == MODE_WGRAD || MODE == MODE_GEMM_TN);
+    constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_WGRAD || MODE == MODE_GEMM_NN || MODE == MODE_GEMM_TN);
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint64_t descA0 = A_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
     const uint64_t descB0 = B_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
@@ -430,6 +442,46 @@ int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int o
   p.splits = 1;
   p.out = D; p.ldo = N; p.out_fp32 = out_fp32;
   return bn == 64 ? launch<64, MODE_GEMM>(ma, mb, p, s) : launch<128, MODE_GEMM>(ma, mb, p, s);
+}
+
+// D[M,N] = A[M,K] * B[K,N]   (A row-major K contiguous, B row-major N contiguous); K need not be a multiple of 64
+int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s) {
+  if (ensure_driver()) return -1;
+  if (N % 128 || K % 8) {
+    fd_set_error("gemm_nn: N must be a multiple of 128 and K of 8", __FILE__, __LINE__);
+    return -1;
+  }
+  CUtensorMap ma, mb;
+  if (make_map_2d(&ma, A, M, K, K, BM) || make_map_2d(&mb, B, K, N, N, 64)) return -1;
+  KParams p{};
+  p.mode = MODE_GEMM_NN;
+  p.M = M; p.N = N;
+  p.num_kb = (K + 63) / 64;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = N / 128;
+  p.splits = 1;
+  p.out = D; p.ldo = N; p.out_fp32 = out_fp32;
+  return launch<128, MODE_GEMM_NN>(ma, mb, p, s);
+}
+
+// D[M,N] = A^T * B with A stored [K,M] (M contiguous) and B stored [K,N] (N contiguous)
+int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s) {
+  if (ensure_driver()) return -1;
+  if (N % 128 || M % 8) {
+    fd_set_error("gemm_tn: N must be a multiple of 128 and M of 8", __FILE__, __LINE__);
+    return -1;
+  }
+  CUtensorMap ma, mb;
+  if (make_map_2d(&ma, A, K, M, M, 64) || make_map_2d(&mb, B, K, N, N, 64)) return -1;
+  KParams p{};
+  p.mode = MODE_GEMM_TN;
+  p.M = M; p.N = N;
+  p.num_kb = (K + 63) / 64;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = N / 128;
+  p.splits = 1;
+  p.out = D; p.ldo = N; p.out_fp32 = out_fp32;
+  return launch<128, MODE_GEMM_TN>(ma, mb, p, s);
 }
 
 int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,

@@ -1092,8 +1092,8 @@ static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
   int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem);
   if (per_sm < 1) return 0;
-  if (per_sm > 2) per_sm = 2;
-  long want = (M * (C / 8) + 1023) / 1024;
+  if (per_sm > 4) per_sm = 4;  // more CTAs = more 16-byte loads in flight (HBM needs ~4.5 MB outstanding)
+  long want = (M * (C / 8) + 511) / 512;
   long cap = (long)sms * per_sm;
   if (want > cap) want = cap;
   if (want < 1) want = 1;

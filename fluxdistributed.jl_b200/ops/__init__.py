@@ -57,5 +57,5 @@ from .reference import (bn_apply_ref, bn_bwd_ref, bn_stats_ref, conv_bn_act_ref,
                         conv_fprop_ref, conv_wgrad_ref, softmax_ce_ref)
 from .native import (bn_apply, bn_bwd, bn_stats, conv3x3_dgrad, conv3x3_fprop, conv3x3_wgrad, conv_bn_act,  # noqa: E402
                      conv_dgrad, conv_fprop, conv_wgrad,
-                     fused_update_local, gap_linear, gemm_nt, maxpool2d, normalize_u8, softmax_ce, stem_fprop, stem_s2d,
+                     fused_update_local, gap_linear, gemm_nn, gemm_nt, gemm_tn, maxpool2d, normalize_u8, softmax_ce, stem_fprop, stem_s2d,
                      stem_wgrad)

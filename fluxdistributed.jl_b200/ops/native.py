@@ -39,6 +39,20 @@ def krsc(w: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- raw kernels
+def gemm_nn(a: torch.Tensor, b: torch.Tensor, out_dtype=BF16) -> torch.Tensor:
+    """``a[M,K] @ b[K,N]`` on tcgen05 (B read N-major)."""
+    d = torch.empty(a.shape[0], b.shape[1], dtype=out_dtype, device=a.device)
+    _ext().gemm_nn(a.contiguous(), b.contiguous(), d)
+    return d
+
+
+def gemm_tn(a: torch.Tensor, b: torch.Tensor, out_dtype=torch.float32) -> torch.Tensor:
+    """``a[K,M]^T @ b[K,N]`` on tcgen05 (both operands MN-major)."""
+    d = torch.empty(a.shape[1], b.shape[1], dtype=out_dtype, device=a.device)
+    _ext().gemm_tn(a.contiguous(), b.contiguous(), d)
+    return d
+
+
 def gemm_nt(a: torch.Tensor, b: torch.Tensor, out_dtype=BF16) -> torch.Tensor:
     """``a[M,K] @ b[N,K]^T`` on tcgen05 (bf16 in, fp32 accumulate)."""
     d = torch.empty(a.shape[0], b.shape[0], dtype=out_dtype, device=a.device)
@@ -422,14 +436,21 @@ class _GapLinear(torch.autograd.Function):
         e = _ext()
         # dW[cls, c] = sum_n d[n, cls] * pooled[n, c]
         gw = w_gradbuf if w_gradbuf is not None else torch.empty(ncls, c, dtype=torch.float32, device=d.device)
-        e.small_gemm(d, pooled, gw, ncls, c, n, 1, ncls, c, 1)
+        tc = c % 128 == 0 and ncls % 8 == 0
+        if tc:
+            e.gemm_tn(d, pooled, gw)        # tcgen05: A = d stored [K=n, M=cls], B = pooled [K=n, N=c]
+        else:
+            e.small_gemm(d, pooled, gw, ncls, c, n, 1, ncls, c, 1)
         gb = None
         if has_b:
             gb = b_gradbuf if b_gradbuf is not None else torch.empty(ncls, dtype=torch.float32, device=d.device)
             e.colsum(d, gb)
         # dpooled[n, c] = sum_cls d[n, cls] * W[cls, c]
         dp = torch.empty(n, c, dtype=BF16, device=d.device)
-        e.small_gemm(d, wl, dp, n, c, ncls, ncls, 1, c, 1)
+        if tc:
+            e.gemm_nn(d, wl.contiguous(), dp)  # tcgen05: d[n, cls] @ W[cls, c]
+        else:
+            e.small_gemm(d, wl, dp, n, c, ncls, ncls, 1, c, 1)
         dx = torch.empty(n, h, ww, c, dtype=BF16, device=d.device)
         e.gap_bwd(dp, dx)
         return (from_nhwc(dx), None if w_gradbuf is not None else gw,
