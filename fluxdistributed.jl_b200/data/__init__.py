@@ -3,7 +3,7 @@
 from .cifar import assemble, cifar_key, cifar_minibatch
 from .imagenet import fproc, labels, makepaths, minibatch, train_solutions
 from .loader import DataLoader, StagedLoader
-from .preprocess import (MEAN, STD, center_crop, decode_image, forward, getweights, load_img, preprocess,
-                         preprocess_u8, resize_smallest_dimension, weights)
+from .preprocess import (MEAN, STD, center_crop, decode_image, forward, getweights, ground_truth, load_img,
+                         make_fname, preprocess, preprocess_u8, resize_smallest_dimension, testimgs, valimgs, weights)
 from .registry import BlobTree, SyntheticTree, dataset, load_registry, open_tree, register
 from .synthetic import SyntheticKey, synthetic_minibatch

@@ -132,3 +132,31 @@ def forward(model: torch.nn.Module, im, **kw) -> torch.Tensor:
         p = next(model.parameters())
         x = preprocess(im, **kw).unsqueeze(0).to(p.device)
         return torch.softmax(model(x).float(), dim=-1)[0]
+
+
+# --------------------------------------------------------------------------- dataset helper stubs (preprocess.jl tail)
+def make_fname(img_id: str, dataset: str = "val", base: str = "ILSVRC/Data/CLS-LOC") -> str:
+    """``make_fname``: path of an image id inside the CLS-LOC layout (same rule as ``imagenet.makepaths``)."""
+    from .imagenet import makepaths
+
+    return makepaths(img_id, dataset, base)
+
+
+def valimgs(tree, csv: str = "LOC_val_solution.csv", classes=None):
+    """``valimgs``: the validation table (ImageId, label, class_idx)."""
+    from .imagenet import train_solutions
+
+    return train_solutions(tree, csv, classes)
+
+
+def testimgs(tree, n: int = 100, prefix: str = "ILSVRC2012_test_"):
+    """``testimgs``: ids of the (unlabelled) test split."""
+    return [f"{prefix}{i + 1:08d}" for i in range(n)]
+
+
+def ground_truth(key, img_id: str) -> int:
+    """``ground_truth``: class index of ``img_id`` in a solutions table."""
+    row = key[key["ImageId"] == img_id]
+    if len(row) == 0:
+        raise KeyError(img_id)
+    return int(row["class_idx"].iloc[0])

@@ -351,6 +351,31 @@ class FusedGroup:
             self.comm.gather_slots(self.replicas)
         return {r.dev: r.state_tree() for r in self.replicas}
 
+    def ensure_synced(self) -> bool:
+        """Replica-consistency check (reference ``ensure_synced``, ``ddp_tasks.jl:115-126``) as a cheap
+        collective: compare a checksum of every replica's compute weights.  Replicas are expected to be
+        bit-identical after every fused step."""
+        def digest(r):
+            a = r.arena
+            w = a.w16 if a.w16 is not None else a.w32
+            v = w.view(torch.int16 if w.element_size() == 2 else torch.int32).to(torch.int64)
+            return int((v * 2654435761 % 4294967291).sum().item())
+
+        sums = [digest(r) for r in self.replicas]
+        if len(self.replicas) == 1:
+            try:
+                import torch.distributed as dist
+
+                if dist.is_initialized() and dist.get_world_size() > 1:
+                    t = torch.tensor([sums[0]], dtype=torch.int64, device=self.replicas[0].dev.torch_device)
+                    lo, hi = t.clone(), t.clone()
+                    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+                    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+                    return bool(lo.item() == hi.item())
+            except Exception:
+                pass
+        return len(set(sums)) == 1
+
     def close(self) -> None:
         self.comm.close()
 

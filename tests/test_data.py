@@ -103,3 +103,14 @@ def test_registry_lookup():
 def test_assemble():
     a = D.assemble([torch.zeros(3, 4), torch.ones(3, 4)])
     assert a.shape == (2, 3, 4)
+
+
+def test_dataset_helper_stubs_and_legacy_alias():
+    import resnetimagenet
+
+    assert resnetimagenet.prepare_training is fd.prepare_training
+    tree = D.SyntheticTree(nclasses=5, ntrain=20, nval=6)
+    v = D.valimgs(tree, classes=range(5))
+    assert len(v) == 6 and D.ground_truth(v, v["ImageId"][0]) == int(v["class_idx"][0])
+    assert D.make_fname("ILSVRC2012_val_00000001").endswith("val/ILSVRC2012_val_00000001.JPEG")
+    assert len(D.testimgs(tree, 3)) == 3

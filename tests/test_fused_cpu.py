@@ -106,3 +106,13 @@ def test_gloo_world2_matches_single():
     for a, b, c in zip(res[0], res[1], ref.parameters()):
         assert torch.equal(a, b)
         assert torch.allclose(a, c, atol=1e-5)
+
+
+def test_ensure_synced_checksum():
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    grp = FusedGroup.for_threads([copy.deepcopy(base) for _ in range(2)], fd.fake_devices(2), fd.Momentum(),
+                                 dtype=torch.float32)
+    assert grp.ensure_synced()
+    grp.replicas[1].arena.w32[3] += 1.0
+    assert not grp.ensure_synced()
