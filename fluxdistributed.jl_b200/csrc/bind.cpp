@@ -106,12 +106,12 @@ void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad) {
                       (int)x.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
         "conv_fprop");
 }
-void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad) {
+void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::optional<at::Tensor> add) {
   want(dy, at::kBFloat16, "dy");
   want(w, at::kBFloat16, "w");
   want(dx, at::kBFloat16, "dx");
   c10::cuda::CUDAGuard guard(dy.device());
-  check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+  check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
                       (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
         "conv_dgrad");
 }
@@ -155,9 +155,9 @@ void bn_bwd(at::Tensor dout, at::Tensor y, c10::optional<at::Tensor> out, at::Te
                   dres.has_value() ? dres->data_ptr() : nullptr, y.numel() / C, C, relu, cur_stream()),
         "bn_bwd");
 }
-void maxpool_fwd(at::Tensor x, at::Tensor out, int k, int stride, int pad) {
+void maxpool_fwd(at::Tensor x, at::Tensor out, c10::optional<at::Tensor> idx, int k, int stride, int pad) {
   c10::cuda::CUDAGuard guard(x.device());
-  check(fd_maxpool_fwd(x.data_ptr(), out.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3), k,
+  check(fd_maxpool_fwd(x.data_ptr(), out.data_ptr(), idx.has_value() ? idx->data_ptr() : nullptr, (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3), k,
                        stride, pad, cur_stream()),
         "maxpool_fwd");
 }
@@ -262,9 +262,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x.size(0), (int)x.size(1),
                            (int)x.size(2), (int)x.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_fprop");
   });
-  m.def("conv3x3_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int variant) {
+  m.def("conv3x3_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int variant, c10::optional<at::Tensor> add) {
     c10::cuda::CUDAGuard guard(dy.device());
-    check(fd_conv3x3_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+    check(fd_conv3x3_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
                            (int)dx.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_dgrad");
   });
   m.def("conv3x3_wgrad", [](at::Tensor dy, at::Tensor x, at::Tensor dw, int splits) {
@@ -321,6 +321,11 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_bwd", &bn_bwd);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("maxpool_bwd_idx", [](at::Tensor idx, at::Tensor dout, at::Tensor dx, int k, int stride, int pad) {
+    c10::cuda::CUDAGuard guard(dx.device());
+    check(fd_maxpool_bwd_idx(idx.data_ptr(), dout.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+                             (int)dx.size(3), k, stride, pad, cur_stream()), "maxpool_bwd_idx");
+  });
   m.def("upsample_zero", [](at::Tensor dy, at::Tensor up, int stride) {
     c10::cuda::CUDAGuard guard(dy.device());
     check(fd_upsample_zero(dy.data_ptr(), up.data_ptr(), (int)dy.size(0), (int)dy.size(1), (int)dy.size(2), (int)up.size(1),

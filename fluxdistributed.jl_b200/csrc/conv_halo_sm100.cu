@@ -39,6 +39,7 @@ struct HParams {
   void* out;
   float* sum;
   float* sumsq;
+  const void* add;  // optional bf16 tensor (same shape as out) added before the store
   int dbg;  // debug/ablation bits: 1 = skip output stores, 2 = skip patch loads, 4 = skip MMAs
 };
 
@@ -274,6 +275,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       for (int q = 0; q < BN / 32; ++q) {
         const int c0 = q * 32;
         uint32_t(&v)[32] = va[q];
+        if (P.add != nullptr && valid) {
+          const bf16* arow = reinterpret_cast<const bf16*>(P.add) + (((long)n * P.H + h) * P.W + w) * P.Nout + n0 + c0;
+#pragma unroll
+          for (int j4 = 0; j4 < 4; ++j4) {
+            const uint4 a = *reinterpret_cast<const uint4*>(arow + j4 * 8);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f2 = unpack_bf16x2(aw[e]);
+              v[j4 * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[j4 * 8 + 2 * e]) + f2.x);
+              v[j4 * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[j4 * 8 + 2 * e + 1]) + f2.y);
+            }
+          }
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -389,8 +404,8 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
 }
 
 template <bool DGRAD>
-int conv3x3_dispatch(const void* in, const void* w, void* out, float* sum, float* sumsq, int N, int H, int W, int Cin,
-                     int Cout, int wcols, int variant, cudaStream_t s) {
+int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, float* sum, float* sumsq, int N, int H,
+                     int W, int Cin, int Cout, int wcols, int variant, cudaStream_t s) {
   // in: [N,H,W,Cin] (x or dy), out: [N,H,W,Cout]; weight matrix rows: K_filter, cols: 9*C_filter (wcols = C_filter)
   if (h_init()) return -1;
   if (Cin % 64 || Cout % 64) {
@@ -401,7 +416,7 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, float* sum, float
   p.N = N; p.H = H; p.W = W; p.Cred = Cin; p.Nout = Cout; p.chunks = Cin / 64;
   p.tiles_h = (H + TH - 1) / TH; p.tiles_w = (W + TW - 1) / TW;
   p.m_tiles = N * p.tiles_h * p.tiles_w;
-  p.wcols = wcols; p.out = out; p.sum = sum; p.sumsq = sumsq;
+  p.wcols = wcols; p.out = out; p.sum = sum; p.sumsq = sumsq; p.add = add;
   p.dbg = variant >> 8; variant &= 255;
   // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
   const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
@@ -750,7 +765,7 @@ int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* su
   p.N = N; p.H = HO; p.W = WO; p.Cred = 256; p.Nout = 64; p.chunks = 4;
   p.tiles_h = (HO + TH - 1) / TH; p.tiles_w = (WO + TW - 1) / TW;
   p.m_tiles = N * p.tiles_h * p.tiles_w; p.n_tiles = 1;
-  p.wcols = 0; p.out = y; p.sum = sum; p.sumsq = sumsq; p.dbg = 0;
+  p.wcols = 0; p.out = y; p.sum = sum; p.sumsq = sumsq; p.dbg = 0; p.add = nullptr;
   CUtensorMap ma, mb;
   if (map_s2d_overlap(&ma, x2, N, HS, WS)) return -1;
   if (map_w(&mb, w2, 64, 256, 64)) return -1;
@@ -811,9 +826,9 @@ int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* s
     FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, K * sizeof(float), s));
     FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, K * sizeof(float), s));
   }
-  return conv3x3_dispatch<false>(x, w, y, sum, sumsq, N, H, W, C, K, C, variant, s);
+  return conv3x3_dispatch<false>(x, w, y, nullptr, sum, sumsq, N, H, W, C, K, C, variant, s);
 }
-int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int variant,
-                     cudaStream_t s) {
-  return conv3x3_dispatch<true>(dy, w, dx, nullptr, nullptr, N, H, W, K, C, C, variant, s);
+int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K,
+                     int variant, cudaStream_t s) {
+  return conv3x3_dispatch<true>(dy, w, dx, add, nullptr, nullptr, N, H, W, K, C, C, variant, s);
 }

@@ -8,16 +8,16 @@ int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int o
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
                   int pad, cudaStream_t s);
-int fd_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int R, int S, int pad,
-                  cudaStream_t s);
+int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
+                  int pad, cudaStream_t s);
 int fd_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int R, int S,
                   int stride, int pad, int splits, int accumulate, cudaStream_t s);
 
 // halo-tile 3x3 / stride-1 / pad-1 kernels (conv_halo_sm100.cu); variant 0 = auto
 int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K,
                      int variant, cudaStream_t s);
-int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int variant,
-                     cudaStream_t s);
+int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K,
+                     int variant, cudaStream_t s);
 int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
                      cudaStream_t s);
 // stem: 7x7/2 conv as a 4x4/1 conv over the space-to-depth input (conv_halo_sm100.cu)

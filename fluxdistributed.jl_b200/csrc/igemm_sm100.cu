@@ -54,6 +54,7 @@ struct KParams {
   long ldo;           // row stride in elements
   int out_fp32;       // 1: float output (store or atomic add)
   int out_atomic;
+  const void* add;    // optional bf16 tensor added to the result before the store (fused residual-gradient sum)
 };
 
 template <int BN, int MODE>
@@ -302,6 +303,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                   for (int e = 0; e < 8; ++e)
                     if (col0 + j + e < P.N) o[j + e] = __float2bfloat16_rn(__uint_as_float(v[j + e]));
                 } else {
+                  if (P.add) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.add) + (long)row * P.ldo + col0 + j);
+                    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float2 f2 = unpack_bf16x2(aw[e]);
+                      v[j + 2 * e] = __float_as_uint(__uint_as_float(v[j + 2 * e]) + f2.x);
+                      v[j + 2 * e + 1] = __float_as_uint(__uint_as_float(v[j + 2 * e + 1]) + f2.y);
+                    }
+                  }
                   uint4 u;
                   u.x = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
                   u.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -510,8 +521,8 @@ int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, in
   return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
 }
 
-int fd_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int R, int S, int pad,
-                  cudaStream_t s) {
+int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
+                  int pad, cudaStream_t s) {
   // stride-1 data gradient: dx[N,H,W,C] from dy[N,P,Q,K]; P = H + 2pad - R + 1
   if (ensure_driver()) return -1;
   if (C % 64 || K % 64) {
@@ -535,7 +546,7 @@ int fd_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, 
   p.splits = 1;
   p.PQ = H * W; p.Q = W; p.stride = 1; p.lower_w = pad - (S - 1); p.lower_h = pad - (R - 1);
   p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
-  p.out = dx; p.ldo = C; p.out_fp32 = 0;
+  p.out = dx; p.ldo = C; p.out_fp32 = 0; p.add = add;
   return bn == 64 ? launch<64, MODE_DGRAD>(ma, mb, p, s) : launch<128, MODE_DGRAD>(ma, mb, p, s);
 }
 

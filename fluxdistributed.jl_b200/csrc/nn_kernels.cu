@@ -561,8 +561,8 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
 // (first maximum in scan order, matching PyTorch) instead of storing indices.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int P, int Q,
-                   int k, int stride, int pad) {
+maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, uint8_t* __restrict__ idx, int N, int H, int W,
+                   int C, int P, int Q, int k, int stride, int pad) {
   const int C8 = C / 8;
   const long total = (long)N * P * Q * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -573,8 +573,12 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, in
     const int p = (int)(t % P);
     const int n = (int)(t / P);
     float m[8];
+    uint32_t am[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+    for (int j = 0; j < 8; ++j) {
+      m[j] = -INFINITY;
+      am[j] = 255u;
+    }
     for (int r = 0; r < k; ++r) {
       const int h = p * stride - pad + r;
       if (h < 0 || h >= H) continue;
@@ -584,8 +588,18 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, in
         float f[8];
         unpack8(ldg8(x + (((long)n * H + h) * W + w) * C + cv * 8), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) m[j] = fmaxf(m[j], f[j]);
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > m[j]) {  // strict: the first maximum in scan order wins, like PyTorch
+            m[j] = f[j];
+            am[j] = (uint32_t)(r * k + s);
+          }
       }
+    }
+    if (idx) {  // one byte per element: window-relative arg-max, consumed by the atomic-free backward
+      uint2 pk;
+      pk.x = am[0] | (am[1] << 8) | (am[2] << 16) | (am[3] << 24);
+      pk.y = am[4] | (am[5] << 8) | (am[6] << 16) | (am[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = pk;
     }
     stg8(out + i * 8, pack8(m));
   }
@@ -642,6 +656,72 @@ maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf
           atomicAdd(reinterpret_cast<bf162*>(base + (long)am[j + 1] * C), __floats2bfloat162_rn(0.f, d[j + 1]));
       }
     }
+  }
+}
+
+// atomic-free max-pool backward: one thread per (input pixel, 8 channels) gathers from the <= ceil(k/stride)^2 windows
+// that contain it, using the arg-max bytes written by the forward kernel.
+__global__ void __launch_bounds__(256)
+maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int H,
+                       int W, int C, int P, int Q, int k, int stride, int pad) {
+  const int C8 = C / 8;
+  const long total = (long)N * H * W * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    long t = i / C8;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float g[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = 0.f;
+    const int p_lo = max(0, (h + pad - k + stride) / stride), p_hi = min(P - 1, (h + pad) / stride);
+    const int q_lo = max(0, (w + pad - k + stride) / stride), q_hi = min(Q - 1, (w + pad) / stride);
+    if (p_hi - p_lo <= 1 && q_hi - q_lo <= 1) {
+      // common case (k <= 2*stride): at most 2x2 windows -> issue all loads first, then combine
+      uint2 pk[4];
+      V8 dv[4];
+      uint32_t pos[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = p_lo + (u >> 1), q = q_lo + (u & 1);
+        ok[u] = (p <= p_hi) && (q <= q_hi);
+        if (ok[u]) {
+          const long oi = (((long)n * P + p) * Q + q) * C8 + cv;
+          pos[u] = (uint32_t)((h - (p * stride - pad)) * k + (w - (q * stride - pad)));
+          pk[u] = *reinterpret_cast<const uint2*>(idx + oi * 8);
+          dv[u] = ldg8(dout + oi * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (!ok[u]) continue;
+        float d[8];
+        unpack8(dv[u], d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t a = ((j < 4 ? pk[u].x : pk[u].y) >> ((j & 3) * 8)) & 255u;
+          if (a == pos[u]) g[j] += d[j];
+        }
+      }
+    } else {
+      for (int p = p_lo; p <= p_hi; ++p)
+        for (int q = q_lo; q <= q_hi; ++q) {
+          const long oi = (((long)n * P + p) * Q + q) * C8 + cv;
+          const uint32_t pos = (uint32_t)((h - (p * stride - pad)) * k + (w - (q * stride - pad)));
+          const uint2 pk = *reinterpret_cast<const uint2*>(idx + oi * 8);
+          float d[8];
+          unpack8(ldg8(dout + oi * 8), d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t a = ((j < 4 ? pk.x : pk.y) >> ((j & 3) * 8)) & 255u;
+            if (a == pos) g[j] += d[j];
+          }
+        }
+    }
+    stg8(dx + i * 8, pack8(g));
   }
 }
 
@@ -973,11 +1053,12 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
   return 0;
 }
 
-int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s) {
+int fd_maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C, int k, int stride, int pad,
+                   cudaStream_t s) {
   const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
   int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 16);
-  maxpool_fwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out), N, H, W, C, P,
-                                          Q, k, stride, pad);
+  maxpool_fwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<bf16*>(out),
+                                          reinterpret_cast<uint8_t*>(idx), N, H, W, C, P, Q, k, stride, pad);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -989,6 +1070,15 @@ int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, i
   int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 16);
   maxpool_bwd_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(dout),
                                           reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q, k, stride, pad);
+  FD_LAUNCH_OK();
+  return 0;
+}
+int fd_maxpool_bwd_idx(const void* idx, const void* dout, void* dx, int N, int H, int W, int C, int k, int stride, int pad,
+                       cudaStream_t s) {
+  const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
+  int grid = grid_for((long)N * H * W * (C / 8), 256, 148 * 16);
+  maxpool_bwd_idx_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(dout),
+                                              reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q, k, stride, pad);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -1093,7 +1183,9 @@ static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, smem);
   if (per_sm < 1) return 0;
   if (per_sm > 4) per_sm = 4;  // more CTAs = more 16-byte loads in flight (HBM needs ~4.5 MB outstanding)
-  long want = (M * (C / 8) + 511) / 512;
+  // one CTA per ~64 KB of input: small layers must not pay for hundreds of same-address atomics and a wide
+  // grid barrier (measured: 592 CTAs cost a fixed ~22 us per launch regardless of tensor size)
+  long want = (M * C * 2 + 65535) / 65536;
   long cap = (long)sms * per_sm;
   if (want > cap) want = cap;
   if (want < 1) want = 1;

@@ -9,7 +9,10 @@ int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, con
 int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C,
               int relu, cudaStream_t s);
-int fd_maxpool_fwd(const void* x, void* out, int N, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
+int fd_maxpool_fwd(const void* x, void* out, void* idx, int N, int H, int W, int C, int k, int stride, int pad,
+                   cudaStream_t s);
+int fd_maxpool_bwd_idx(const void* idx, const void* dout, void* dx, int N, int H, int W, int C, int k, int stride, int pad,
+                       cudaStream_t s);
 int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, int N, int H, int W, int C, int k,
                    int stride, int pad, cudaStream_t s);
 int fd_upsample_zero(const void* dy, void* up, int N, int P, int Q, int HU, int WU, int C, int stride, cudaStream_t s);

@@ -88,7 +88,7 @@ class ConvBN(nn.Module):
         if zero_init:
             nn.init.zeros_(self.bn.weight)
 
-    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, add_link=None, res_link=None) -> torch.Tensor:
         if _use_native(x):
             from ..ops import conv_bn_act
             from ..ops.native import bn_workspace
@@ -101,7 +101,8 @@ class ConvBN(nn.Module):
                                self.bn.eps, self.bn.momentum, self.training,
                                getattr(self.conv.weight, "_lowp", None),
                                (getattr(self.conv.weight, "_gradbuf", None), getattr(self.bn.weight, "_gradbuf", None),
-                                getattr(self.bn.bias, "_gradbuf", None)), ws)
+                                getattr(self.bn.bias, "_gradbuf", None)), ws,
+                               add_link, res_link)
         w = self.conv.weight
         if x.dtype != w.dtype:
             w = w.to(x.dtype)

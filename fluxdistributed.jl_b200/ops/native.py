@@ -86,11 +86,12 @@ def conv3x3_fprop(x: torch.Tensor, w: torch.Tensor, stats: bool = False, variant
     return (from_nhwc(y), s, ss) if stats else from_nhwc(y)
 
 
-def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, variant: int = 0) -> torch.Tensor:
+def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, variant: int = 0, add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``add`` (same shape as the result) is summed into dx in the epilogue (fused residual-gradient accumulation)."""
     dyh, wk = nhwc(dy), krsc(w)
     n, h, ww, _ = dyh.shape
     dx = torch.empty(n, h, ww, wk.shape[3], dtype=BF16, device=dy.device)
-    _ext().conv3x3_dgrad(dyh, wk, dx, variant)
+    _ext().conv3x3_dgrad(dyh, wk, dx, variant, None if add is None else nhwc(add))
     return from_nhwc(dx)
 
 
@@ -144,7 +145,8 @@ def stem_wgrad(dy: torch.Tensor, x2: torch.Tensor, out: Optional[torch.Tensor] =
     return out
 
 
-def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int) -> torch.Tensor:
+def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
+               add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Data gradient.  Stride 1 runs the tcgen05 dgrad directly; stride 2 zero-upsamples ``dy``
     (``dy_up[2i,2j] = dy[i,j]``) and reuses the stride-1 kernel."""
     n, c, h, ww = x_shape
@@ -156,7 +158,7 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int
         _ext().upsample_zero(dyh, up, stride)
         dyh = up
     dx = torch.empty(n, h, ww, c, dtype=BF16, device=dy.device)
-    _ext().conv_dgrad(dyh, wk, dx, pad)
+    _ext().conv_dgrad(dyh, wk, dx, pad, None if add is None else nhwc(add))
     return from_nhwc(dx)
 
 
@@ -302,7 +304,12 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                w_gradbuf, bn_ws=None):
+                w_gradbuf, bn_ws=None, add_link=None, res_link=None):
+        # add_link / res_link: a dict shared by the two convs of a residual block.  The conv that consumes the
+        # skip input (`res_link`) parks its residual gradient there instead of returning it, and the conv that
+        # reads the block input (`add_link`) sums it into dx inside the dgrad epilogue — one tensor add per block
+        # that autograd would otherwise launch as a separate elementwise kernel.
+        ctx.add_link, ctx.res_link = add_link, res_link
         wl = w_lowp if w_lowp is not None else w.detach().to(BF16)
         if not wl.permute(0, 2, 3, 1).is_contiguous():
             wl = wl.contiguous(memory_format=torch.channels_last)
@@ -352,16 +359,22 @@ class _ConvBNAct(torch.autograd.Function):
                                              dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf, beta=beta)
         if ctx.g_gradbuf is not None:  # landed in the arena: autograd must not accumulate them again
             dgamma = dbeta = None
+        if has_res and ctx.res_link is not None:
+            ctx.res_link["dres"] = dres  # picked up by the block's first conv (runs later in the backward pass)
+            dres = None
         dx = None
         if ctx.needs_input_grad[0]:
+            add = ctx.add_link.pop("dres", None) if ctx.add_link is not None else None
             if k3 and _halo_fprop_ok(w_shape[0], w_shape[1], x_shape[2]):
-                dx = conv3x3_dgrad(dy, wl)
+                dx = conv3x3_dgrad(dy, wl, add=add)
             elif tc:
-                dx = conv_dgrad(dy, wl, x_shape, stride, pad)
+                dx = conv_dgrad(dy, wl, x_shape, stride, pad, add=add)
             elif stem:
                 dx = torch.nn.grad.conv2d_input(ctx.orig_shape, wl, dy, stride, pad)
             else:
                 dx = torch.nn.grad.conv2d_input(x_shape, wl, dy, stride, pad)
+                if add is not None:
+                    dx = dx + add
         if stem:
             gw = stem_wgrad(dy, x, out=ctx.w_gradbuf)  # x holds the s2d tensor here
         elif k3 and x_shape[2] >= 14:
@@ -376,13 +389,13 @@ class _ConvBNAct(torch.autograd.Function):
         # when the gradient already landed in the arena, autograd must not add it a second time
         dw = None if ctx.w_gradbuf is not None else gw
         return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
-                None, None, None)
+                None, None, None, None, None)
 
 
 def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
-                w_gradbuf=None, bn_ws=None):
+                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None):
     return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                            w_gradbuf, bn_ws)
+                            w_gradbuf, bn_ws, add_link, res_link)
 
 
 # --------------------------------------------------------------------------- autograd: max-pool, GAP + FC
@@ -393,16 +406,18 @@ class _MaxPool(torch.autograd.Function):
         n, h, w, c = xh.shape
         p, q = (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
         out = torch.empty(n, p, q, c, dtype=x.dtype, device=x.device)
-        _ext().maxpool_fwd(xh, out, k, stride, pad)
-        ctx.save_for_backward(xh, out)
-        ctx.cfg = (k, stride, pad)
+        idx = torch.empty(n, p, q, c, dtype=torch.uint8, device=x.device)  # window-relative arg-max, 1 byte/element
+        _ext().maxpool_fwd(xh, out, idx, k, stride, pad)
+        ctx.save_for_backward(idx)
+        ctx.cfg = (k, stride, pad, tuple(xh.shape))
         return from_nhwc(out)
 
     @staticmethod
     def backward(ctx, dout):
-        xh, out = ctx.saved_tensors
-        dx = torch.empty_like(xh)
-        _ext().maxpool_bwd(xh, out, nhwc(dout.to(xh.dtype)), dx, *ctx.cfg)
+        (idx,) = ctx.saved_tensors
+        k, stride, pad, xshape = ctx.cfg
+        dx = torch.empty(xshape, dtype=BF16, device=idx.device)
+        _ext().maxpool_bwd_idx(idx, nhwc(dout.to(BF16)), dx, k, stride, pad)  # gather: no atomics, no memset
         return from_nhwc(dx), None, None, None
 
 

@@ -31,5 +31,12 @@ for hw, C in [(112, 64), (56, 64), (28, 128), (14, 256), (7, 512)]:
     t = timeit(lambda i: (lambda: ops.bn_apply(ys[i], s, ss, gamma, beta, 1e-5, residual=ds[i]))); r["apply_res_us"] = round(t, 1); r["apply_res_GBs"] = round(3 * V / t * 1e3)
     t = timeit(lambda i: (lambda: ops.bn_bwd(ds[i], ys[i], None, mean, rstd, gamma, True, beta=beta))); r["bwd_us"] = round(t, 1); r["bwd_GBs"] = round(5 * V / t * 1e3)
     t = timeit(lambda i: (lambda: ops.bn_bwd(ds[i], ys[i], out, mean, rstd, gamma, True, want_dres=True, beta=beta))); r["bwd_res_us"] = round(t, 1); r["bwd_res_GBs"] = round(8 * V / t * 1e3)
+    from fluxdist.ops import native as N
+    wss = [N.bn_workspace(C, "cuda") for _ in range(NSET)]
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    t = timeit(lambda i: (lambda: N.bn_fwd_fused(ys[i], gamma, beta, 1e-5, wss[i], None, True, rm, rv))); r["F_fwd_us"] = round(t, 1); r["F_fwd_GBs"] = round(3 * V / t * 1e3)
+    t = timeit(lambda i: (lambda: N.bn_fwd_fused(ys[i], gamma, beta, 1e-5, wss[i], ds[i], True, rm, rv))); r["F_fwd_res_us"] = round(t, 1)
+    t = timeit(lambda i: (lambda: N.bn_bwd_fused(ds[i], ys[i], None, mean, rstd, gamma, beta, wss[i], True))); r["F_bwd_us"] = round(t, 1); r["F_bwd_GBs"] = round(5 * V / t * 1e3)
+    t = timeit(lambda i: (lambda: N.bn_bwd_fused(ds[i], ys[i], out, mean, rstd, gamma, beta, wss[i], True, want_dres=True))); r["F_bwd_res_us"] = round(t, 1)
     t = timeit(lambda i: (lambda: ys[i].add_(ds[i]))); r["torch_add_us"] = round(t, 1); r["torch_add_GBs"] = round(3 * V / t * 1e3)
     print(json.dumps(r), flush=True)
