@@ -213,6 +213,52 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
     return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
 
 
+SIDE_WGRAD = True  # run weight-gradient kernels on a side stream (they are off the backward critical path)
+_SIDE = {}
+_SIDE_PENDING = set()
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    s = _SIDE.get(key)
+    if s is None:
+        s = _SIDE[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+def join_side_stream(device=None) -> None:
+    """Make the current stream wait for weight-gradient work queued on the side stream."""
+    if not _SIDE_PENDING:
+        return
+    for key in list(_SIDE_PENDING):
+        if device is not None and key != (device.index if device.index is not None else torch.cuda.current_device()):
+            continue
+        torch.cuda.current_stream(torch.device("cuda", key)).wait_stream(_SIDE[key])
+        _SIDE_PENDING.discard(key)
+
+
+def _on_side_stream(fn, tensors):
+    """Fork: run ``fn`` on the side stream after everything queued so far on the current stream; the join happens
+    at the end of the backward pass (autograd callback) or before the fused update.  In backward, wgrad only feeds
+    the optimiser, so its tcgen05 work can overlap the bandwidth-bound BN-backward / dgrad chain of earlier layers."""
+    dev = tensors[0].device
+    side = _side_stream(dev)
+    cur = torch.cuda.current_stream(dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    for x in tensors:
+        x.record_stream(side)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_PENDING:
+        _SIDE_PENDING.add(key)
+        try:
+            torch.autograd.Variable._execution_engine.queue_callback(lambda: join_side_stream(dev))
+        except Exception:
+            pass
+    return out
+
+
 BN_FUSED = True  # single-launch grid-barrier BN kernels (disabled when replicas share one physical GPU)
 
 
@@ -375,12 +421,16 @@ class _ConvBNAct(torch.autograd.Function):
                 dx = torch.nn.grad.conv2d_input(x_shape, wl, dy, stride, pad)
                 if add is not None:
                     dx = dx + add
+        side = SIDE_WGRAD and ctx.w_gradbuf is not None and dy.is_cuda
         if stem:
-            gw = stem_wgrad(dy, x, out=ctx.w_gradbuf)  # x holds the s2d tensor here
+            fn = lambda: stem_wgrad(dy, x, out=ctx.w_gradbuf)  # x holds the s2d tensor here
+            gw = _on_side_stream(fn, (dy, x)) if side else fn()
         elif k3 and x_shape[2] >= 14:
-            gw = conv3x3_wgrad(dy, x, out=ctx.w_gradbuf)
+            fn = lambda: conv3x3_wgrad(dy, x, out=ctx.w_gradbuf)
+            gw = _on_side_stream(fn, (dy, x)) if side else fn()
         elif tc:
-            gw = conv_wgrad(dy, x, w_shape, stride, pad, out=ctx.w_gradbuf)
+            fn = lambda: conv_wgrad(dy, x, w_shape, stride, pad, out=ctx.w_gradbuf)
+            gw = _on_side_stream(fn, (dy, x)) if side else fn()
         else:
             gw = torch.nn.grad.conv2d_weight(x.float(), w_shape, dy.float(), stride, pad)
             if ctx.w_gradbuf is not None:

@@ -127,6 +127,10 @@ class FusedReplica:
 
     def reduce_and_update(self) -> None:
         assert self.group is not None
+        if self.dev.is_cuda:
+            from ..ops import native as _native
+
+            _native.join_side_stream(self.dev.torch_device)  # weight gradients queued on the side stream
         self.step_count += 1
         self.group.comm.allreduce_update(self)
 
