@@ -213,7 +213,9 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
     return from_nhwc(dy), dgamma, dbeta, (from_nhwc(dres) if want_dres else None)
 
 
-SIDE_WGRAD = True  # run weight-gradient kernels on a side stream (they are off the backward critical path)
+import os as _os
+
+SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
 _SIDE_PENDING = set()
 

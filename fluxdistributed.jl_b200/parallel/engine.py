@@ -67,7 +67,9 @@ class GraphedStep:
             torch.cuda.synchronize(rep.dev.torch_device)
             n0 = ops.extension().launch_count() if ops.native_available() else 0
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
+            # an explicit per-replica capture stream: torch's default capture stream is a process-wide singleton bound
+            # to whichever device used it first, which breaks concurrent captures from several replica threads
+            with torch.cuda.graph(self.graph, stream=s, capture_error_mode=self.capture_error_mode):
                 self._body()
             self.launches_per_step = (ops.extension().launch_count() - n0) if ops.native_available() else 0
             self._captured = True

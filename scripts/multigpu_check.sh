@@ -22,7 +22,8 @@ grep -m3 -i "nvls" gpurun_out/allreduce_x$N.log | cut -c1-200
 tail -1 gpurun_out/allreduce_x$N.jsonl
 python - <<PY
 import json
-rows=[json.loads(l) for l in open("gpurun_out/allreduce_x$N.jsonl") if '"variant"' in l]
+rows=[json.loads(l) for l in open("gpurun_out/allreduce_x$N.jsonl")]
+rows=[r for r in rows if "variant" in r and "bytes" in r]
 sizes=sorted({r["bytes"] for r in rows})
 print("bytes        " + "  ".join(f"{v:>16s}" for v in ["fused/p2p","fused/nvls","fused/oneshot","nccl+opt"]))
 for s in sizes:
