@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--hw", type=int, default=224)
+    ap.add_argument("--mode", default="process", choices=["process", "task"],
+                    help="process: one rank per GPU (torchrun); task: ONE process drives --gpus GPUs with a thread per GPU")
     return ap.parse_args()
 
 
@@ -50,6 +52,64 @@ def reference_arm():
     if os.path.isdir(ref_dir) and os.listdir(ref_dir):
         why = "baseline/_ref present but the reference is Julia code; no Julia runtime in this image"
     print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+def task_mode(args):
+    """Task-based parallelism (reference README.md:21-52): one process, one thread and one CUDA graph per GPU, the fused
+    kernel exchanging gradients through UVA peer pointers.  Same timing rules as the process mode."""
+    import copy
+    from concurrent.futures import ThreadPoolExecutor
+
+    import torch
+
+    import fluxdist as fd
+    from fluxdist.parallel import FusedGroup
+    from fluxdist.parallel.engine import graphed_replica_step
+
+    n = args.gpus
+    fd.nn.set_backend("native")
+    torch.manual_seed(0)
+    ctor = {"resnet18": fd.models.ResNet18, "resnet34": fd.models.ResNet34, "resnet50": fd.models.ResNet50}
+    base = ctor.get(args.model, fd.models.ResNet34)(1000).to(memory_format=torch.channels_last)
+    devs = fd.cuda_devices(n)
+    opt = fd.Momentum(0.01, 0.9) if args.opt == "momentum" else fd.ADAM()
+    models = [copy.deepcopy(base).to(d.torch_device) for d in devs]
+    grp = FusedGroup.for_threads(models, devs, opt, loss=fd.logitcrossentropy, comm="native")
+    B, K, W, hw = args.batch, args.steps, max(args.warmup, 3), args.hw
+    xs = [torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, device=d.torch_device) for d in devs]
+    ys = [torch.randint(0, 1000, (B,), device=d.torch_device) for d in devs]
+    pool = ThreadPoolExecutor(n)
+
+    def one(i):
+        return graphed_replica_step(grp.replicas[i], xs[i], ys[i], fd.logitcrossentropy)
+
+    def step_all():
+        return [f.result() for f in [pool.submit(one, i) for i in range(n)]]
+
+    for _ in range(W):
+        step_all()
+    for d in devs:
+        torch.cuda.synchronize(d.torch_device)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in devs]
+    for (a, _), d in zip(ev, devs):
+        with torch.cuda.device(d.torch_device):
+            a.record(torch.cuda.current_stream(d.torch_device))
+    for _ in range(K):
+        out = step_all()
+    for (_, b), d in zip(ev, devs):
+        with torch.cuda.device(d.torch_device):
+            b.record(torch.cuda.current_stream(d.torch_device))
+    for d in devs:
+        torch.cuda.synchronize(d.torch_device)
+    ms = max(a.elapsed_time(b) for a, b in ev)
+    rec = {"metric": "ResNet-34 ImageNet-shape training throughput", "value": B * n * K / (ms / 1e3), "unit": "images/sec",
+           "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "bf16", "data": "synthetic (device-resident uint8 images)", "impl": "native",
+           "config": {"model": args.model, "global_batch": B * n, "parallelism": f"dp{n}", "mode": "task (1 process, thread per GPU)",
+                      "comm": getattr(grp.replicas[0], "comm_info", {})},
+           "final_loss": float(out[0].item()), "synced": grp.ensure_synced()}
+    print(json.dumps(rec))
+    return 0
 
 
 def main():
@@ -64,6 +124,8 @@ def main():
     import fluxdist as fd
     from fluxdist.utils.tracing import ClockSampler
 
+    if args.mode == "task":
+        return task_mode(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
