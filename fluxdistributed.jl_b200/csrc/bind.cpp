@@ -115,6 +115,15 @@ void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::option
                       (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
         "conv_dgrad");
 }
+void conv_dgrad_s2(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::optional<at::Tensor> add_compact) {
+  want(dy, at::kBFloat16, "dy");
+  want(w, at::kBFloat16, "w");
+  want(dx, at::kBFloat16, "dx");
+  c10::cuda::CUDAGuard guard(dy.device());
+  check(fd_conv_dgrad_s2(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add_compact), (int)dx.size(0), (int)dx.size(1),
+                         (int)dx.size(2), (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
+        "conv_dgrad_s2");
+}
 void conv_wgrad(at::Tensor dy, at::Tensor x, at::Tensor dw, int stride, int pad, int splits, bool accumulate) {
   want(dy, at::kBFloat16, "dy");
   want(x, at::kBFloat16, "x");
@@ -255,6 +264,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("conv_fprop", &conv_fprop);
   m.def("conv_dgrad", &conv_dgrad);
+  m.def("conv_dgrad_s2", &conv_dgrad_s2);
   m.def("conv_wgrad", &conv_wgrad);
   m.def("conv3x3_fprop", [](at::Tensor x, at::Tensor w, at::Tensor y, c10::optional<at::Tensor> sum,
                             c10::optional<at::Tensor> sumsq, int variant) {
@@ -355,6 +365,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                          cur_stream()), "probe_shift");
   });
   m.def("num_sms", &fd_num_sms);
+  m.def("set_cluster_multicast", &fd_set_cluster_multicast);
   m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
   fd_bind_staging(m);
 }

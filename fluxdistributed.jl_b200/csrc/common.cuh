@@ -289,6 +289,35 @@ FD_DEVINL void tma_load_im2col_4d_p(void* smem_dst, const void* desc, uint64_t* 
       "l"(desc), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h), "r"(issue)
       : "memory");
 }
+// ---- thread-block clusters: rank, barrier, multicast TMA, multicast commit
+FD_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+FD_DEVINL void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// one tile lands at the same CTA-relative smem offset of every CTA in `mask`, and signals the mbarrier at the same
+// CTA-relative offset in each of them
+FD_DEVINL void tma_load_2d_mc_p(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, uint16_t mask,
+                                uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster "
+      "[%0], [%1, {%3, %4}], [%2], %5;\n\t}" ::"r"(smem_u32(smem_dst)),
+      "l"(desc), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask), "r"(issue)
+      : "memory");
+}
+FD_DEVINL void umma_commit_mc_p(uint64_t* bar, uint16_t mask, uint32_t issue) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::
+          "r"(smem_u32(bar)),
+      "h"(mask), "r"(issue)
+      : "memory");
+}
+
 // warp-uniform broadcast of a value every lane already holds (tells the compiler it is uniform)
 FD_DEVINL uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 int fd_num_sms();
+void fd_set_cluster_multicast(int on);  // 2-CTA cluster + TMA multicast of the filter tile in conv fprop/dgrad (default on)
 int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
@@ -10,6 +11,11 @@ int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, in
                   int pad, cudaStream_t s);
 int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
                   int pad, cudaStream_t s);
+// stride-2 data gradient without a zero-upsampled tensor: 4 output-parity classes, each a stride-1 correlation with the
+// taps that reach it (R,S <= 3; H,W even).  `add_compact` ([N,H/2,W/2,C], optional) is summed into the (even,even) class:
+// it carries the data gradient of a parallel 1x1/stride-2 projection.  Parity classes no tap reaches are NOT written.
+int fd_conv_dgrad_s2(const void* dy, const void* w, void* dx, const void* add_compact, int N, int H, int W, int C, int K,
+                     int R, int S, int pad, cudaStream_t s);
 int fd_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int R, int S,
                   int stride, int pad, int splits, int accumulate, cudaStream_t s);
 

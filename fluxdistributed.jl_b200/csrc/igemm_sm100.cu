@@ -17,6 +17,7 @@
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+TMEM alloc), 2..5 = epilogue.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -32,7 +33,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // bf16 elements per k-block = one 128B swizzle row
 constexpr int kThreads = 192;
 
-enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_WGRAD = 3, MODE_GEMM_NN = 4, MODE_GEMM_TN = 5 };
+enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_WGRAD = 3, MODE_GEMM_NN = 4, MODE_GEMM_TN = 5, MODE_DGRAD_S2 = 6 };
 
 struct KParams {
   int mode;
@@ -55,6 +56,16 @@ struct KParams {
   int out_fp32;       // 1: float output (store or atomic add)
   int out_atomic;
   const void* add;    // optional bf16 tensor added to the result before the store (fused residual-gradient sum)
+  // stride-2 data gradient (MODE_DGRAD_S2): the output is split into its 4 (h%2, w%2) parity classes; each class is a
+  // stride-1 correlation of dy with the subset of filter taps that hit that parity (1+2+2+4 = 9 taps for a 3x3 filter:
+  // no zero-upsampled tensor, no multiplications by zero).  Classes ride on the `splits` tile dimension.
+  int sub_ntaps[4];           // taps of class c
+  unsigned char sub_ow[4][4]; // im2col offsets (relative to the lower corner) of tap t of class c
+  unsigned char sub_oh[4][4];
+  unsigned char sub_wi[4][4]; // filter tap index r*S+s
+  unsigned char sub_ph[4], sub_pw[4];  // output parity of class c
+  int sub_H, sub_W;           // full-resolution output extent
+  int sub_add_cls;            // class that receives `add` (a COMPACT [N,H/2,W/2,C] tensor), -1: none
 };
 
 template <int BN, int MODE>
@@ -67,7 +78,11 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * BN;  // double-buffered accumulator
 };
 
-template <int BN, int MODE>
+// MC = true: 2-CTA thread-block cluster along M.  The two CTAs work on neighbouring m-tiles of the same n-tile, so
+// they need the same B (filter) tile: each CTA fetches HALF of it and the copy engine multicasts it into both CTAs'
+// shared memory (.multicast::cluster), halving the L2 traffic of the operand that every m-tile re-reads.  Shared-memory
+// slots are released cluster-wide (tcgen05.commit ... .multicast::cluster on both CTAs' empty barriers).
+template <int BN, int MODE, bool MC = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams P) {
   using C = Cfg<BN, MODE>;
@@ -92,7 +107,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     tma_prefetch_desc(&mapB);
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], MC ? 2 : 1);  // cluster mode: both CTAs must have consumed a slot before either refills it
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -106,24 +121,31 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync();  // peers' barriers are initialised before any remote arrive / multicast copy
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  const int crank = MC ? (int)cluster_ctarank() : 0;
 
-  const int total_tiles = P.m_tiles * P.n_tiles * P.splits;
+  // cluster mode iterates over pairs of m-tiles; CTA `crank` of the pair owns m-tile 2*pair + crank (an m-tile past the
+  // end is harmless: its loads are TMA zero-fill and the epilogue masks its rows)
+  const int m_units = MC ? (P.m_tiles + 1) / 2 : P.m_tiles;
+  const int total_tiles = m_units * P.n_tiles * P.splits;
+  const int t_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================================================== TMA producer (convergent warp, lane 0 issues)
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int split = t / (P.m_tiles * P.n_tiles);
-        int rem = t - split * (P.m_tiles * P.n_tiles);
-        const int mt = rem / P.n_tiles, nt = rem % P.n_tiles;
+      for (int t = t_first; t < total_tiles; t += t_step) {
+        int split = t / (m_units * P.n_tiles);
+        int rem = t - split * (m_units * P.n_tiles);
+        const int mt = (MC ? 2 : 1) * (rem / P.n_tiles) + crank, nt = rem % P.n_tiles;
         const int m0 = mt * BM, n0 = nt * BN;
         // base pixel of this tile (conv modes)
         int bn = 0, bh = 0, bw = 0;
-        if (MODE == MODE_FPROP || MODE == MODE_DGRAD) {
+        if (MODE == MODE_FPROP || MODE == MODE_DGRAD || MODE == MODE_DGRAD_S2) {
           bn = m0 / P.PQ;
           int r2 = m0 - bn * P.PQ;
           int p = r2 / P.Q, q = r2 - p * P.Q;
@@ -132,6 +154,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         }
         int kb_begin = 0, kb_end = P.num_kb;
         int tap = 0;
+        if (MODE == MODE_DGRAD_S2) kb_end = P.sub_ntaps[split] * P.C_chunks;
         if (MODE == MODE_WGRAD) {
           // n-tile index enumerates (tap, c-chunk); split enumerates pixel ranges
           tap = nt / P.C_chunks;
@@ -145,7 +168,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           mbar_arrive_expect_tx_p(&full[stage], C::STAGE_BYTES, leader);
           if (MODE == MODE_GEMM) {
             tma_load_2d_p(a, &mapA, &full[stage], kb * BK, m0, leader);
-            tma_load_2d_p(b, &mapB, &full[stage], kb * BK, n0, leader);
+            if (MC)
+              tma_load_2d_mc_p(b + crank * (BN / 2) * 128, &mapB, &full[stage], kb * BK, n0 + crank * (BN / 2), 3, leader);
+            else
+              tma_load_2d_p(b, &mapB, &full[stage], kb * BK, n0, leader);
           } else if (MODE == MODE_GEMM_NN) {  // A[M,K] K-major, B[K,N] N-major
             tma_load_2d_p(a, &mapA, &full[stage], kb * BK, m0, leader);
 #pragma unroll
@@ -162,7 +188,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             const int tp = kb / P.C_chunks, cc = kb - tp * P.C_chunks;
             const int r = tp / P.S, s = tp - r * P.S;
             tma_load_im2col_4d_p(a, &mapA, &full[stage], cc * BK, bw, bh, bn, (uint16_t)s, (uint16_t)r, leader);
-            tma_load_2d_p(b, &mapB, &full[stage], tp * P.Ctot + cc * BK, n0, leader);
+            if (MC)
+              tma_load_2d_mc_p(b + crank * (BN / 2) * 128, &mapB, &full[stage], tp * P.Ctot + cc * BK,
+                               n0 + crank * (BN / 2), 3, leader);
+            else
+              tma_load_2d_p(b, &mapB, &full[stage], tp * P.Ctot + cc * BK, n0, leader);
           } else if (MODE == MODE_DGRAD) {
             // reduction over (tap, k-chunk); A = im2col(dY) with flipped taps, B = W[k, (r,s,c)] (N-major)
             const int tp = kb / P.C_chunks, kc = kb - tp * P.C_chunks;
@@ -172,6 +202,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j)
               tma_load_2d_p(b + j * (BK * 128), &mapB, &full[stage], tp * P.Ctot + n0 + j * 64, kc * BK, leader);
+          } else if (MODE == MODE_DGRAD_S2) {
+            const int tp = kb / P.C_chunks, kc = kb - tp * P.C_chunks;
+            const int wi = P.sub_wi[split][tp];
+            tma_load_im2col_4d_p(a, &mapA, &full[stage], kc * BK, bw, bh, bn, (uint16_t)P.sub_ow[split][tp],
+                                 (uint16_t)P.sub_oh[split][tp], leader);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d_p(b + j * (BK * 128), &mapB, &full[stage], wi * P.Ctot + n0 + j * 64, kc * BK, leader);
           } else {  // WGRAD: A = dY[pixels, k] (M-major), B = im2col(X)[pixels, c] (N-major), both 64-pixel k-blocks
             const int cc = nt - tap * P.C_chunks;
             const int r = tap / P.S, s = tap - r * P.S;
@@ -195,7 +233,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===================================================== MMA issuer
     constexpr bool A_MN = (MODE == MODE_WGRAD || MODE == MODE_GEMM_TN);
-    constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_WGRAD || MODE == MODE_GEMM_NN || MODE == MODE_GEMM_TN);
+    constexpr bool B_MN = (MODE == MODE_DGRAD || MODE == MODE_DGRAD_S2 || MODE == MODE_WGRAD || MODE == MODE_GEMM_NN || MODE == MODE_GEMM_TN);
     constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
     const uint64_t descA0 = A_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
     const uint64_t descB0 = B_MN ? umma_smem_desc(0, BK * 128, 1024, UMMA_LAYOUT_SW128) : umma_smem_desc(0, 16, 1024, UMMA_LAYOUT_SW128);
@@ -204,10 +242,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = t_first; t < total_tiles; t += t_step) {
       int kb_count = P.num_kb;
+      if (MODE == MODE_DGRAD_S2) kb_count = P.sub_ntaps[t / (m_units * P.n_tiles)] * P.C_chunks;
       if (MODE == MODE_WGRAD) {
-        int split = t / (P.m_tiles * P.n_tiles);
+        int split = t / (m_units * P.n_tiles);
         int b0 = (int)(((long)P.kb_total * split) / P.splits);
         int b1 = (int)(((long)P.kb_total * (split + 1)) / P.splits);
         kb_count = b1 - b0;
@@ -229,7 +268,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           for (int k = 0; k < BK / 16; ++k)
             umma_f16_ss_p(d_tmem, da0 + (uint64_t)(k * (A_MN ? 128 : 2)), db0 + (uint64_t)(k * (B_MN ? 128 : 2)), idesc,
                           (kb > 0 || k > 0) ? 1u : 0u, leader);
-          umma_commit_p(&empty[stage], leader);                         // smem slot free once these MMAs retire
+          if (MC) umma_commit_mc_p(&empty[stage], 3, leader);           // release the slot in both CTAs of the cluster
+          else umma_commit_p(&empty[stage], leader);                    // smem slot free once these MMAs retire
           if (kb == kb_count - 1) umma_commit_p(&tfull[acc], leader);   // accumulator ready for the epilogue
         }
         if (++stage == kStages) {
@@ -246,10 +286,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      int split = t / (P.m_tiles * P.n_tiles);
-      int rem = t - split * (P.m_tiles * P.n_tiles);
-      const int mt = rem / P.n_tiles, nt = rem % P.n_tiles;
+    for (int t = t_first; t < total_tiles; t += t_step) {
+      int split = t / (m_units * P.n_tiles);
+      int rem = t - split * (m_units * P.n_tiles);
+      const int mt = (MC ? 2 : 1) * (rem / P.n_tiles) + crank, nt = rem % P.n_tiles;
       const int m0 = mt * BM;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -294,7 +334,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                 }
               }
             } else {
-              bf16* o = reinterpret_cast<bf16*>(P.out) + (long)row * P.ldo + col0;
+              long orow = row;  // row of the output matrix this accumulator row lands in
+              bool use_add = P.add != nullptr;
+              if (MODE == MODE_DGRAD_S2) {
+                const int n_ = row / P.PQ, r2 = row - n_ * P.PQ;
+                const int i_ = r2 / P.Q, j_ = r2 - i_ * P.Q;
+                orow = ((long)n_ * P.sub_H + 2 * i_ + P.sub_ph[split]) * P.sub_W + 2 * j_ + P.sub_pw[split];
+                use_add = use_add && split == P.sub_add_cls;
+              }
+              bf16* o = reinterpret_cast<bf16*>(P.out) + orow * P.ldo + col0;
               const bool vec = (P.ldo & 7) == 0;
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -303,7 +351,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
                   for (int e = 0; e < 8; ++e)
                     if (col0 + j + e < P.N) o[j + e] = __float2bfloat16_rn(__uint_as_float(v[j + e]));
                 } else {
-                  if (P.add) {
+                  if (use_add) {
                     const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.add) + (long)row * P.ldo + col0 + j);
                     const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
@@ -334,6 +382,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync();  // no CTA may exit while its peer can still multicast into it or arrive on its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -431,6 +480,31 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStr
   return 0;
 }
 
+template <int BN, int MODE>
+int launch_mc(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStream_t s) {
+  using C = Cfg<BN, MODE>;
+  FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * p.splits;
+  int clusters = g_num_sms / 2;
+  if (clusters > pairs) clusters = pairs;
+  if (clusters < 1) clusters = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FD_CUDA_CHECK(cudaLaunchKernelEx(&cfg, igemm_kernel<BN, MODE, true>, a, b, p));
+  fd_count_launch();
+  return 0;
+}
+
 }  // namespace
 
 int fd_num_sms() { return g_num_sms; }
@@ -458,10 +532,11 @@ int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int o
 // D[M,N] = A[M,K] * B[K,N]   (A row-major K contiguous, B row-major N contiguous); K need not be a multiple of 64
 int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s) {
   if (ensure_driver()) return -1;
-  if (N % 128 || K % 8) {
-    fd_set_error("gemm_nn: N must be a multiple of 128 and K of 8", __FILE__, __LINE__);
+  if (N % 64 || K % 8) {
+    fd_set_error("gemm_nn: N must be a multiple of 64 and K of 8", __FILE__, __LINE__);
     return -1;
   }
+  const int bn = (N % 128 == 0) ? 128 : 64;
   CUtensorMap ma, mb;
   if (make_map_2d(&ma, A, M, K, K, BM) || make_map_2d(&mb, B, K, N, N, 64)) return -1;
   KParams p{};
@@ -469,10 +544,10 @@ int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int o
   p.M = M; p.N = N;
   p.num_kb = (K + 63) / 64;
   p.m_tiles = (M + BM - 1) / BM;
-  p.n_tiles = N / 128;
+  p.n_tiles = N / bn;
   p.splits = 1;
   p.out = D; p.ldo = N; p.out_fp32 = out_fp32;
-  return launch<128, MODE_GEMM_NN>(ma, mb, p, s);
+  return bn == 64 ? launch<64, MODE_GEMM_NN>(ma, mb, p, s) : launch<128, MODE_GEMM_NN>(ma, mb, p, s);
 }
 
 // D[M,N] = A^T * B with A stored [K,M] (M contiguous) and B stored [K,N] (N contiguous)
@@ -495,6 +570,9 @@ int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int o
   return launch<128, MODE_GEMM_TN>(ma, mb, p, s);
 }
 
+static int g_use_mc = 1;
+void fd_set_cluster_multicast(int on) { g_use_mc = on; }
+
 int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
                   int pad, cudaStream_t s) {
   if (ensure_driver()) return -1;
@@ -507,7 +585,10 @@ int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, in
   CUtensorMap ma, mb;
   // bounding box of base pixels: [-pad, dim-1 + pad-(R-1)] (CUTLASS compute_{lower,upper}_corner_whd, fprop)
   if (make_map_im2col(&ma, x, N, H, W, C, -pad, -pad, pad - (S - 1), pad - (R - 1), stride, BM)) return -1;
-  if (make_map_2d(&mb, w, K, (long)R * S * C, (long)R * S * C, bn)) return -1;
+  // cluster + multicast pays only when every SM pair has at least two full waves of m-tiles (measured on B200,
+  // profiles/cluster_multicast_fprop.json: 28x28x128 25.0 -> 24.2 us; a loss below ~2 waves)
+  const bool mc = g_use_mc && bn == 128 && ((long)N * P_ * Q_ + BM - 1) / BM >= 2L * g_num_sms;
+  if (make_map_2d(&mb, w, K, (long)R * S * C, (long)R * S * C, mc ? bn / 2 : bn)) return -1;
   KParams p{};
   p.mode = MODE_FPROP;
   p.M = N * P_ * Q_; p.N = K;
@@ -518,6 +599,7 @@ int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, in
   p.PQ = P_ * Q_; p.Q = Q_; p.stride = stride; p.lower_w = -pad; p.lower_h = -pad;
   p.S = S; p.R = R; p.C_chunks = C / 64; p.Ctot = C;
   p.out = y; p.ldo = K; p.out_fp32 = 0;
+  if (mc) return launch_mc<128, MODE_FPROP>(ma, mb, p, s);
   return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
 }
 
@@ -548,6 +630,72 @@ int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int 
   p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
   p.out = dx; p.ldo = C; p.out_fp32 = 0; p.add = add;
   return bn == 64 ? launch<64, MODE_DGRAD>(ma, mb, p, s) : launch<128, MODE_DGRAD>(ma, mb, p, s);
+}
+
+int fd_conv_dgrad_s2(const void* dy, const void* w, void* dx, const void* add_compact, int N, int H, int W, int C, int K,
+                     int R, int S, int pad, cudaStream_t s) {
+  // stride-2 data gradient by output-parity decomposition: dx[N,H,W,C] from dy[N,H/2,W/2,K], filter [K,R,S,C], R,S <= 3.
+  // Output pixel h = 2i+ph receives tap r iff (ph + pad - r) is even, from dy row i + (ph + pad - r)/2.
+  if (ensure_driver()) return -1;
+  const int P_ = (H + 2 * pad - R) / 2 + 1, Q_ = (W + 2 * pad - S) / 2 + 1;
+  if (C % 64 || K % 64 || R > 3 || S > 3 || (H & 1) || (W & 1) || P_ != H / 2 || Q_ != W / 2) {
+    fd_set_error("conv_dgrad_s2: unsupported geometry", __FILE__, __LINE__);
+    return -1;
+  }
+  const int bn = (C % 128 == 0) ? 128 : 64;
+  int lo_h = 0, lo_w = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int r = 0; r < R; ++r)
+      if (((ph + pad - r) & 1) == 0) lo_h = std::min(lo_h, (ph + pad - r) / 2);
+  for (int pw = 0; pw < 2; ++pw)
+    for (int q = 0; q < S; ++q)
+      if (((pw + pad - q) & 1) == 0) lo_w = std::min(lo_w, (pw + pad - q) / 2);
+  KParams p{};
+  struct Cls { int ph, pw, n; unsigned char ow[4], oh[4], wi[4]; } cls[4];
+  int ncls = 0;
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      Cls c{ph, pw, 0, {0}, {0}, {0}};
+      for (int r = 0; r < R; ++r)
+        for (int q = 0; q < S; ++q)
+          if (((ph + pad - r) & 1) == 0 && ((pw + pad - q) & 1) == 0) {
+            c.oh[c.n] = (unsigned char)((ph + pad - r) / 2 - lo_h);
+            c.ow[c.n] = (unsigned char)((pw + pad - q) / 2 - lo_w);
+            c.wi[c.n] = (unsigned char)(r * S + q);
+            ++c.n;
+          }
+      cls[ncls++] = c;
+    }
+  std::sort(cls, cls + 4, [](const Cls& a, const Cls& b) { return a.n > b.n; });  // longest tiles first
+  p.sub_add_cls = -1;
+  int used = 0;
+  for (int i = 0; i < 4; ++i) {
+    if (cls[i].n == 0) continue;  // parity classes no tap reaches (1x1 filters): the caller pre-zeroes dx
+    p.sub_ntaps[used] = cls[i].n;
+    p.sub_ph[used] = (unsigned char)cls[i].ph;
+    p.sub_pw[used] = (unsigned char)cls[i].pw;
+    for (int t = 0; t < 4; ++t) {
+      p.sub_ow[used][t] = cls[i].ow[t];
+      p.sub_oh[used][t] = cls[i].oh[t];
+      p.sub_wi[used][t] = cls[i].wi[t];
+    }
+    if (cls[i].ph == 0 && cls[i].pw == 0 && add_compact) p.sub_add_cls = used;
+    ++used;
+  }
+  CUtensorMap ma, mb;
+  if (make_map_im2col(&ma, dy, N, P_, Q_, K, lo_w, lo_h, lo_w, lo_h, 1, BM)) return -1;
+  if (make_map_2d(&mb, w, K, (long)R * S * C, (long)R * S * C, 64)) return -1;
+  p.mode = MODE_DGRAD_S2;
+  p.M = N * P_ * Q_; p.N = C;
+  p.num_kb = 0;
+  p.m_tiles = (p.M + BM - 1) / BM;
+  p.n_tiles = C / bn;
+  p.splits = used;
+  p.PQ = P_ * Q_; p.Q = Q_; p.stride = 1; p.lower_w = lo_w; p.lower_h = lo_h;
+  p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
+  p.sub_H = H; p.sub_W = W;
+  p.out = dx; p.ldo = C; p.out_fp32 = 0; p.add = (p.sub_add_cls >= 0) ? add_compact : nullptr;
+  return bn == 64 ? launch<64, MODE_DGRAD_S2>(ma, mb, p, s) : launch<128, MODE_DGRAD_S2>(ma, mb, p, s);
 }
 
 int fd_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int R, int S,

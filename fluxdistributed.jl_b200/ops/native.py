@@ -7,6 +7,7 @@ PyTorch oracle in ``ops/reference.py``; ``tests/test_native_gpu.py`` compares th
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -145,13 +146,33 @@ def stem_wgrad(dy: torch.Tensor, x2: torch.Tensor, out: Optional[torch.Tensor] =
     return out
 
 
+S2_NATIVE = os.environ.get("FLUXDIST_S2_DGRAD", "1") != "0"
+
+
+def _s2_native_ok(h: int, ww: int, r: int, s: int, pad: int) -> bool:
+    return (S2_NATIVE and r <= 3 and s <= 3 and h % 2 == 0 and ww % 2 == 0
+            and (h + 2 * pad - r) // 2 + 1 == h // 2 and (ww + 2 * pad - s) // 2 + 1 == ww // 2)
+
+
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
-               add: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Data gradient.  Stride 1 runs the tcgen05 dgrad directly; stride 2 zero-upsamples ``dy``
-    (``dy_up[2i,2j] = dy[i,j]``) and reuses the stride-1 kernel."""
+               add: Optional[torch.Tensor] = None, add_compact: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient.  Stride 1 runs the tcgen05 dgrad directly.  Stride 2 (1x1 / 3x3 filters, even images) runs the
+    parity-decomposed kernel: each (h%2, w%2) class of dx is a stride-1 correlation of dy with the taps that reach it,
+    so neither a zero-upsampled copy of dy nor multiplications by its zeros exist.  ``add_compact`` ([N,C,H/2,W/2]) is
+    summed into the (even, even) class: the data gradient of a parallel 1x1/stride-2 projection (ResNet downsample).
+    Other strided geometries zero-upsample ``dy`` and reuse the stride-1 kernel."""
     n, c, h, ww = x_shape
     dyh, wk = nhwc(dy), krsc(w)
     k, r, s, _ = wk.shape
+    if stride == 2 and add is None and _s2_native_ok(h, ww, r, s, pad):
+        full = all(any((p + pad - t) % 2 == 0 for t in range(r)) for p in (0, 1)) and \
+            all(any((p + pad - t) % 2 == 0 for t in range(s)) for p in (0, 1))
+        alloc = torch.empty if full else torch.zeros  # classes no tap reaches (1x1 filters) stay zero
+        dx = alloc(n, h, ww, c, dtype=BF16, device=dy.device)
+        _ext().conv_dgrad_s2(dyh, wk, dx, pad, None if add_compact is None else nhwc(add_compact))
+        return from_nhwc(dx)
+    if add_compact is not None:
+        raise ValueError("add_compact needs the native stride-2 dgrad")
     if stride != 1:
         hu, wu = h + 2 * pad - r + 1, ww + 2 * pad - s + 1
         up = torch.empty(n, hu, wu, k, dtype=BF16, device=dy.device)
@@ -352,7 +373,11 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                w_gradbuf, bn_ws=None, add_link=None, res_link=None):
+                w_gradbuf, bn_ws=None, add_link=None, res_link=None, park_link=None):
+        # park_link: given to a 1x1/stride-2 projection shortcut whose input is also read by a stride-2 3x3 conv that
+        # got the same dict as add_link.  The projection parks its data gradient as a COMPACT [N,H/2,W/2,C] tensor (a
+        # plain GEMM) and the 3x3's parity-decomposed dgrad sums it into its (even, even) class.
+        ctx.park_link = park_link
         # add_link / res_link: a dict shared by the two convs of a residual block.  The conv that consumes the
         # skip input (`res_link`) parks its residual gradient there instead of returning it, and the conv that
         # reads the block input (`add_link`) sums it into dx inside the dgrad epilogue — one tensor add per block
@@ -413,10 +438,20 @@ class _ConvBNAct(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             add = ctx.add_link.pop("dres", None) if ctx.add_link is not None else None
+            addc = ctx.add_link.pop("dcompact", None) if ctx.add_link is not None else None
+            if ctx.add_link is not None and ctx.add_link.get("expect_compact") and addc is None:
+                ctx.add_link["late"] = True  # the projection has not run yet: it must return its own dx
+            park = ctx.park_link
             if k3 and _halo_fprop_ok(w_shape[0], w_shape[1], x_shape[2]):
                 dx = conv3x3_dgrad(dy, wl, add=add)
+            elif tc and park is not None and not park.get("late") and stride == 2 and w_shape[2] == 1 \
+                    and _s2_native_ok(x_shape[2], x_shape[3], 1, 1, pad):
+                dyh = nhwc(dy)
+                park["dcompact"] = from_nhwc(
+                    gemm_nn(dyh.reshape(-1, dyh.shape[3]), krsc(wl).reshape(w_shape[0], w_shape[1]))
+                    .view(dyh.shape[0], dyh.shape[1], dyh.shape[2], w_shape[1]))
             elif tc:
-                dx = conv_dgrad(dy, wl, x_shape, stride, pad, add=add)
+                dx = conv_dgrad(dy, wl, x_shape, stride, pad, add=add, add_compact=addc)
             elif stem:
                 dx = torch.nn.grad.conv2d_input(ctx.orig_shape, wl, dy, stride, pad)
             else:
@@ -441,13 +476,13 @@ class _ConvBNAct(torch.autograd.Function):
         # when the gradient already landed in the arena, autograd must not add it a second time
         dw = None if ctx.w_gradbuf is not None else gw
         return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
-                None, None, None, None, None)
+                None, None, None, None, None, None)
 
 
 def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
-                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None):
+                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None, park_link=None):
     return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                            w_gradbuf, bn_ws, add_link, res_link)
+                            w_gradbuf, bn_ws, add_link, res_link, park_link)
 
 
 # --------------------------------------------------------------------------- autograd: max-pool, GAP + FC

@@ -95,7 +95,15 @@ class NativeComm:
             rep = FusedReplica(m, d, opt, n, i, lowp, sort_lowp_first=True)
             rep._native_comm = comm
             reps.append(rep)
-        grid = min(MAX_GRID, max(1, reps[0].arena.padded // (512 * 2 * 4 * max(n, 1)) + 1))
+        share = max(cu.count(c) for c in set(cu))
+        if share > 1:
+            # virtual replicas on one physical GPU (tests, 1-GPU development): their kernels spin on each other, so
+            # (a) all of them must be co-resident -> bound the grid; (b) nothing a replica still has to do before its
+            # launch may need the context to go idle (lazy module loading does) -> host rendezvous before the launch
+            import threading
+
+            comm._shared_gpu = threading.Barrier(n)
+            comm.max_grid = max(1, 148 // share)
         aux = []
         for rep in reps:
             with device_ctx(rep.dev):
@@ -196,7 +204,7 @@ class NativeComm:
         plan = ext.FusedPlan(self.world, rep.rank, rep.opt.rule_id, mode, use_nvls, n, boundary, list(g_ptrs),
                              a.w32.data_ptr(), s0, s1, wout32, wout16, list(flag_ptrs), aux["epoch"].data_ptr(),
                              aux["step"].data_ptr(), aux["done"].data_ptr(), aux["status"].data_ptr(), mc[0], mc[1],
-                             mc[2], MAX_GRID, rep.dev.cuda_index)
+                             mc[2], getattr(self, "max_grid", MAX_GRID), rep.dev.cuda_index)
         plan.set_hyper(_hyper(rep.opt), 1.0)
         self.plans[id(rep)] = (plan, aux, mode, use_nvls)
         rep.comm_info = dict(mode="one_shot" if mode == MODE_ONE_SHOT else "two_shot", nvls=bool(use_nvls),
@@ -205,6 +213,10 @@ class NativeComm:
     # ------------------------------------------------------------------ runtime
     def allreduce_update(self, rep: FusedReplica) -> None:
         plan, aux, _, _ = self.plans[id(rep)]
+        bar = getattr(self, "_shared_gpu", None)
+        if bar is not None and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream(rep.dev.torch_device).synchronize()
+            bar.wait(timeout=120)
         plan.launch()  # on the replica's current stream; graph-capturable
 
     def set_opt(self, rep: FusedReplica, opt: Rule) -> None:

@@ -88,6 +88,73 @@ def test_conv_dgrad(N, H, W, C, K, R, stride, pad):
     assert rel_err(dx, ref) < 1e-2
 
 
+S2_CASES = [
+    # N, H, W, C, K, R, pad
+    (2, 16, 16, 64, 128, 3, 1),
+    (3, 28, 28, 128, 256, 3, 1),
+    (96, 14, 14, 256, 512, 3, 1),
+    (2, 56, 56, 64, 128, 1, 0),
+    (2, 12, 20, 128, 64, 3, 1),
+    (2, 16, 16, 64, 64, 2, 0),
+]
+
+
+@pytest.mark.parametrize("N,H,W,C,K,R,pad", S2_CASES)
+@pytest.mark.parametrize("with_add", [False, True])
+def test_conv_dgrad_stride2_parity(N, H, W, C, K, R, pad, with_add):
+    """Parity-decomposed stride-2 dgrad (no zero-upsampling) == fp32 reference, incl. the fused compact addend."""
+    from fluxdist.ops import native as NV
+
+    assert NV._s2_native_ok(H, W, R, R, pad)
+    x, w = _conv_data(N, H, W, C, K, R)
+    dy = cl(torch.randn(N, K, H // 2, W // 2, device="cuda").to(BF))
+    addc = cl(torch.randn(N, C, H // 2, W // 2, device="cuda").to(BF)) if with_add else None
+    n0 = ops.extension().launch_count()
+    dx = ops.conv_dgrad(dy, w, (N, C, H, W), 2, pad, add_compact=addc)
+    assert ops.extension().launch_count() - n0 == 1  # one launch: no upsample kernel
+    ref = REF.conv_dgrad_ref(dy, w, (N, C, H, W), 2, pad).float()
+    if with_add:
+        ref[:, :, ::2, ::2] += addc.float()
+    assert rel_err(dx, ref) < 1e-2
+
+
+def test_projection_block_gradients_match_unlinked():
+    """BasicBlock with a projection shortcut: the linked backward (compact 1x1 dgrad summed inside the 3x3/2 dgrad)
+    gives the same input / weight gradients as the unlinked formulation."""
+    from fluxdist.models.resnet import BasicBlock
+    from fluxdist.nn import set_backend
+    from fluxdist.ops import native as NV
+
+    torch.manual_seed(0)
+    set_backend("native")
+    blk = BasicBlock(64, 128, stride=2).cuda().to(memory_format=torch.channels_last)
+    x = cl(torch.randn(4, 64, 32, 32, device="cuda").to(BF)).requires_grad_(True)
+    g = cl(torch.randn(4, 128, 16, 16, device="cuda").to(BF))
+
+    def run():
+        for p_ in blk.parameters():
+            p_.grad = None
+        x.grad = None
+        blk(x).backward(g)
+        torch.cuda.synchronize()
+        return [x.grad.float().clone()] + [p_.grad.float().clone() for p_ in blk.parameters()]
+
+    linked = run()
+    NV.S2_NATIVE = False  # falls back to: zero-upsample + stride-1 dgrad, autograd sums the two branches
+    try:
+        blk2_forward = BasicBlock.forward
+        def plain(self, x_):
+            return self.conv2(self.conv1(x_), residual=self.downsample(x_))
+        BasicBlock.forward = plain
+        unlinked = run()
+    finally:
+        BasicBlock.forward = blk2_forward
+        NV.S2_NATIVE = True
+        set_backend("auto")
+    for a, b in zip(linked, unlinked):
+        assert rel_err(a, b) < 2e-2
+
+
 @pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", CONV_CASES)
 def test_conv_wgrad(N, H, W, C, K, R, stride, pad):
     x, w = _conv_data(N, H, W, C, K, R)
@@ -388,7 +455,8 @@ def test_fused_update_virtual_replicas_one_gpu(mode, opt):
             g, _ = gradient(lambda mm: fd.logitcrossentropy(mm(x), y), ref)
             ref, st = opt(ref, g, st)
     torch.cuda.synchronize()
-    assert all(grp.comm.status(r) == (False, False) for r in grp.replicas)
+    stat = [grp.comm.status(r) for r in grp.replicas]  # (non-finite gradient seen, barrier timed out)
+    assert all(s == (False, False) for s in stat), stat
     grp.sync_to_modules()
     for r in grp.replicas:
         for a, b in zip(r.model.parameters(), ref.parameters()):
