@@ -97,12 +97,13 @@ void gemm_nt(at::Tensor A, at::Tensor B, at::Tensor D) {
         "gemm_nt");
 }
 // x: [N,H,W,C] bf16 (physical NHWC), w: [K,R,S,C] bf16, y: [N,P,Q,K] bf16
-void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad) {
+void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad, c10::optional<at::Tensor> sum,
+                c10::optional<at::Tensor> sumsq) {
   want(x, at::kBFloat16, "x");
   want(w, at::kBFloat16, "w");
   want(y, at::kBFloat16, "y");
   c10::cuda::CUDAGuard guard(x.device());
-  check(fd_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+  check(fd_conv_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x.size(0), (int)x.size(1), (int)x.size(2),
                       (int)x.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
         "conv_fprop");
 }
@@ -146,12 +147,14 @@ void bn_stats(at::Tensor y, at::Tensor sum, at::Tensor sumsq) {
 void bn_apply(at::Tensor y, c10::optional<at::Tensor> res, at::Tensor out, at::Tensor sum, at::Tensor sumsq,
               at::Tensor gamma, at::Tensor beta, c10::optional<at::Tensor> run_mean,
               c10::optional<at::Tensor> run_var, c10::optional<at::Tensor> save_mean,
-              c10::optional<at::Tensor> save_rstd, double eps, double momentum, bool training, bool relu) {
+              c10::optional<at::Tensor> save_rstd, double eps, double momentum, bool training, bool relu,
+              c10::optional<at::Tensor> consumed) {
   c10::cuda::CUDAGuard guard(y.device());
   const int C = (int)gamma.numel();
+  unsigned* cons = consumed.has_value() ? reinterpret_cast<unsigned*>(consumed->data_ptr()) : nullptr;
   check(fd_bn_apply(y.data_ptr(), optptr(res), out.data_ptr(), sum.data_ptr<float>(), sumsq.data_ptr<float>(),
                     gamma.data_ptr<float>(), beta.data_ptr<float>(), optf(run_mean), optf(run_var), optf(save_mean),
-                    optf(save_rstd), y.numel() / C, C, (float)eps, (float)momentum, training, relu, cur_stream()),
+                    optf(save_rstd), y.numel() / C, C, (float)eps, (float)momentum, training, relu, cons, cur_stream()),
         "bn_apply");
 }
 void bn_bwd(at::Tensor dout, at::Tensor y, c10::optional<at::Tensor> out, at::Tensor mean, at::Tensor rstd,
@@ -294,9 +297,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     c10::cuda::CUDAGuard guard(dw.device());
     check(fd_stem_dw_from_s2d(dw2.data_ptr<float>(), dw.data_ptr<float>(), (int)dw.size(0), cur_stream()), "stem_dw_from_s2d");
   });
-  m.def("stem_fprop", [](at::Tensor x2, at::Tensor w2, at::Tensor y, c10::optional<at::Tensor> sum, c10::optional<at::Tensor> sumsq) {
+  m.def("stem_fprop", [](at::Tensor x2, at::Tensor w2, at::Tensor y, c10::optional<at::Tensor> sum, c10::optional<at::Tensor> sumsq,
+                         bool prezeroed) {
     c10::cuda::CUDAGuard guard(x2.device());
-    check(fd_stem_fprop(x2.data_ptr(), w2.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x2.size(0), (int)x2.size(1),
+    check(fd_stem_fprop(x2.data_ptr(), w2.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), prezeroed ? 1 : 0, (int)x2.size(0), (int)x2.size(1),
                         (int)x2.size(2), cur_stream()), "stem_fprop");
   });
   m.def("stem_wgrad", [](at::Tensor dy, at::Tensor x2, at::Tensor dw2) {

@@ -753,11 +753,11 @@ int map_s2d_overlap(CUtensorMap* m, const void* base, int N, int HS, int WS) {
 }  // namespace
 
 // x2: [N, 115, 115, 16] bf16 (space-to-depth of the padded 224x224x3 image), w2: [64, 256] bf16, y: [N,112,112,64]
-int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int N, int HS, int WS,
+int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int prezeroed, int N, int HS, int WS,
                   cudaStream_t s) {
   if (h_init()) return -1;
   const int HO = HS - 3, WO = WS - 3;
-  if (sum) {
+  if (sum && !prezeroed) {
     FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, 64 * sizeof(float), s));
     FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, 64 * sizeof(float), s));
   }
@@ -822,7 +822,9 @@ int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int
 
 int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K,
                      int variant, cudaStream_t s) {
-  if (sum) {
+  const bool prezeroed = (variant & 0x100) != 0;  // the statistics buffers are known to be zero (see bn_apply's `consumed`)
+  variant &= 0xff;
+  if (sum && !prezeroed) {
     FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, K * sizeof(float), s));
     FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, K * sizeof(float), s));
   }

@@ -7,7 +7,7 @@ void fd_set_cluster_multicast(int on);  // 2-CTA cluster + TMA multicast of the 
 int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
-int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
+int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K, int R, int S, int stride,
                   int pad, cudaStream_t s);
 int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
                   int pad, cudaStream_t s);
@@ -27,5 +27,6 @@ int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, i
 int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
                      cudaStream_t s);
 // stem: 7x7/2 conv as a 4x4/1 conv over the space-to-depth input (conv_halo_sm100.cu)
-int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int N, int HS, int WS, cudaStream_t s);
+int fd_stem_fprop(const void* x2, const void* w2, void* y, float* sum, float* sumsq, int prezeroed, int N, int HS, int WS,
+                  cudaStream_t s);
 int fd_stem_wgrad(const void* dy, const void* x2, float* dw2, int N, int HS, int WS, cudaStream_t s);

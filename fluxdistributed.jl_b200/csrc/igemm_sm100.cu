@@ -66,7 +66,26 @@ struct KParams {
   unsigned char sub_ph[4], sub_pw[4];  // output parity of class c
   int sub_H, sub_W;           // full-resolution output extent
   int sub_add_cls;            // class that receives `add` (a COMPACT [N,H/2,W/2,C] tensor), -1: none
+  // fprop: per-output-channel sum / sum of squares of the fp32 accumulators, added atomically (fused BN statistics)
+  float* st_sum;
+  float* st_sq;
 };
+
+// 32x32 transpose-reduce across a warp: lane l holds v[0..31] (row l of a 32-row block); on return v[0] of lane l is the
+// sum over all 32 lanes of their v[l] (column l).  31 shuffles instead of 32 x 5.
+FD_DEVINL float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
 
 template <int BN, int MODE>
 struct Cfg {
@@ -286,11 +305,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
+    const bool do_stats = (MODE == MODE_FPROP) && P.st_sum != nullptr;
+    float st_s[BN / 32], st_q[BN / 32];  // this lane's channel (c0 + lane) of each 32-column chunk, over this CTA's tiles
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) st_s[i] = st_q[i] = 0.f;
+    int st_nt = -1;
+    auto flush_stats = [&]() {
+      if (st_nt >= 0) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          atomicAdd(P.st_sum + st_nt * BN + i * 32 + lane, st_s[i]);
+          atomicAdd(P.st_sq + st_nt * BN + i * 32 + lane, st_q[i]);
+          st_s[i] = st_q[i] = 0.f;
+        }
+      }
+    };
     for (int t = t_first; t < total_tiles; t += t_step) {
       int split = t / (m_units * P.n_tiles);
       int rem = t - split * (m_units * P.n_tiles);
       const int mt = (MC ? 2 : 1) * (rem / P.n_tiles) + crank, nt = rem % P.n_tiles;
       const int m0 = mt * BM;
+      if (do_stats && nt != st_nt) {
+        flush_stats();
+        st_nt = nt;
+      }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
@@ -305,6 +343,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
+        if (do_stats) {  // rows past M are TMA zero-fill: they add nothing
+          float f[32], q[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            f[j] = __uint_as_float(v[j]);
+            q[j] = f[j] * f[j];
+          }
+          st_s[c0 / 32] += warp_column_sums(f, lane);
+          st_q[c0 / 32] += warp_column_sums(q, lane);
+        }
         if (row < P.M && has_k) {
           if (MODE == MODE_WGRAD) {
             // row = output channel k; columns = (tap, c) block: out[k][tap*Ctot + cc*BN + c]
@@ -378,6 +426,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+    if (do_stats) flush_stats();
   }
 
   tc_fence_before();
@@ -573,8 +622,8 @@ int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int o
 static int g_use_mc = 1;
 void fd_set_cluster_multicast(int on) { g_use_mc = on; }
 
-int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, int C, int K, int R, int S, int stride,
-                  int pad, cudaStream_t s) {
+int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K, int R,
+                  int S, int stride, int pad, cudaStream_t s) {
   if (ensure_driver()) return -1;
   if (C % 64 || K % 64) {
     fd_set_error("conv_fprop: C and K must be multiples of 64", __FILE__, __LINE__);
@@ -599,6 +648,7 @@ int fd_conv_fprop(const void* x, const void* w, void* y, int N, int H, int W, in
   p.PQ = P_ * Q_; p.Q = Q_; p.stride = stride; p.lower_w = -pad; p.lower_h = -pad;
   p.S = S; p.R = R; p.C_chunks = C / 64; p.Ctot = C;
   p.out = y; p.ldo = K; p.out_fp32 = 0;
+  p.st_sum = sum; p.st_sq = sumsq;  // accumulated into: the caller provides zeroed buffers
   if (mc) return launch_mc<128, MODE_FPROP>(ma, mb, p, s);
   return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
 }

@@ -92,11 +92,12 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const bf16* __restrict__ 
 // (training) or running stats (eval). Block 0 also emits saved mean/rstd and updates running stats.
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* __restrict__ out,
-                const float* __restrict__ sum, const float* __restrict__ sumsq, const float* __restrict__ gamma,
+                float* sum, float* sumsq, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ run_mean, float* __restrict__ run_var,
                 float* __restrict__ save_mean, float* __restrict__ save_rstd, long M, int C, float eps,
-                float momentum, int training, int relu) {
+                float momentum, int training, int relu, unsigned* consumed) {
   extern __shared__ float smem[];  // scale[C], shift[C]
+  __shared__ int s_last;
   float* sc = smem;
   float* sh = smem + C;
   const float invM = 1.f / (float)M;
@@ -124,6 +125,20 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
     }
   }
   __syncthreads();
+  if (consumed) {
+    // the statistics were accumulated by the producing conv's epilogue into buffers that must be zero again before
+    // its next launch: every CTA counts itself once it has read them; the last one clears them (no waiting involved)
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(consumed, 1u);
+      s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) sum[c] = sumsq[c] = 0.f;
+      if (threadIdx.x == 0) *consumed = 0u;
+    }
+  }
   const int C8 = C / 8;
   const long total = M * C8;
   const long stride = (long)gridDim.x * blockDim.x;
@@ -1021,13 +1036,13 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
   return 0;
 }
 
-int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, const float* sumsq, const float* gamma,
+int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
-                float eps, float momentum, int training, int relu, cudaStream_t s) {
+                float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s) {
   int grid = grid_for(M * (C / 8), 256 * 2, 148 * 8);
   bn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res), reinterpret_cast<bf16*>(out), sum, sumsq,
-      gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu);
+      gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu, consumed);
   FD_LAUNCH_OK();
   return 0;
 }

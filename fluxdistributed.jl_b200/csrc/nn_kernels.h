@@ -3,9 +3,10 @@
 #include <cuda_runtime.h>
 
 int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStream_t s);
-int fd_bn_apply(const void* y, const void* res, void* out, const float* sum, const float* sumsq, const float* gamma,
+// `consumed` (optional): device counter; the last CTA that has read sum/sumsq zeroes them for the producer's next launch
+int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
-                float eps, float momentum, int training, int relu, cudaStream_t s);
+                float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s);
 int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C,
               int relu, cudaStream_t s);
@@ -32,7 +33,8 @@ int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s);
 int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s);
 #define FD_BN_MAX_GRID 296
 // workspace bytes for the single-launch BN kernels with at most `C` channels
-inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)4 * C * sizeof(float); }
+// [barrier counter, generation, stats-consumed counter, pad] + 2 x [2][C] barrier-kernel accumulators + [2][C] epilogue statistics
+inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)6 * C * sizeof(float); }
 int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,
                     float momentum, int relu, cudaStream_t s);

@@ -61,26 +61,37 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out_dtype=BF16) -> torch.Tensor:
     return d
 
 
-def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int) -> torch.Tensor:
-    """``x`` NCHW/channels_last bf16, ``w`` [K,C,R,S]/channels_last bf16 -> y (same convention)."""
+def conv_fprop(x: torch.Tensor, w: torch.Tensor, stride: int, pad: int, stats=None):
+    """``x`` NCHW/channels_last bf16, ``w`` [K,C,R,S]/channels_last bf16 -> y (same convention).
+    ``stats``: ``True`` -> also return per-channel (sum, sum of squares) of the fp32 accumulators, reduced in the
+    epilogue (fused BN statistics); a ``(sum, sumsq)`` pair of ZEROED fp32 buffers -> accumulate into them."""
     xh, wk = nhwc(x), krsc(w)
     n, h, ww, _ = xh.shape
     k, r, s, _ = wk.shape
     p, q = (h + 2 * pad - r) // stride + 1, (ww + 2 * pad - s) // stride + 1
     y = torch.empty(n, p, q, k, dtype=BF16, device=x.device)
-    _ext().conv_fprop(xh, wk, y, stride, pad)
-    return from_nhwc(y)
+    if stats is None or stats is False:
+        _ext().conv_fprop(xh, wk, y, stride, pad, None, None)
+        return from_nhwc(y)
+    sm, sq = (torch.zeros(k, dtype=torch.float32, device=x.device), torch.zeros(k, dtype=torch.float32, device=x.device)) \
+        if stats is True else stats
+    _ext().conv_fprop(xh, wk, y, stride, pad, sm, sq)
+    return from_nhwc(y), sm, sq
 
 
-def conv3x3_fprop(x: torch.Tensor, w: torch.Tensor, stats: bool = False, variant: int = 0):
+def conv3x3_fprop(x: torch.Tensor, w: torch.Tensor, stats=False, variant: int = 0):
     """Halo-tile 3x3/stride-1/pad-1 forward conv; with ``stats`` also returns the per-channel
-    (sum, sum of squares) of the bf16 output accumulated in the epilogue (fused BN statistics)."""
+    (sum, sum of squares) of the bf16 output accumulated in the epilogue (fused BN statistics).
+    ``stats`` may be a ``(sum, sumsq)`` pair of ZEROED buffers to accumulate into (no memset is issued)."""
     xh, wk = nhwc(x), krsc(w)
     n, h, ww, _ = xh.shape
     k = wk.shape[0]
     y = torch.empty(n, h, ww, k, dtype=BF16, device=x.device)
     s = ss = None
-    if stats:
+    if isinstance(stats, tuple):
+        s, ss = stats
+        variant |= 0x100
+    elif stats:
         s = torch.empty(k, dtype=torch.float32, device=x.device)
         ss = torch.empty(k, dtype=torch.float32, device=x.device)
     _ext().conv3x3_fprop(xh, wk, y, s, ss, variant)
@@ -127,10 +138,13 @@ def stem_fprop(x2: torch.Tensor, w: torch.Tensor, stats: bool = False):
     n, hs, ws, _ = x2.shape
     y = torch.empty(n, hs - 3, ws - 3, 64, dtype=BF16, device=x2.device)
     s = ss = None
-    if stats:
+    pre = isinstance(stats, tuple)
+    if pre:
+        s, ss = stats
+    elif stats:
         s = torch.empty(64, dtype=torch.float32, device=x2.device)
         ss = torch.empty(64, dtype=torch.float32, device=x2.device)
-    _ext().stem_fprop(x2, w2, y, s, ss)
+    _ext().stem_fprop(x2, w2, y, s, ss, pre)
     return (from_nhwc(y), s, ss) if stats else from_nhwc(y)
 
 
@@ -209,14 +223,16 @@ def bn_stats(y: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def bn_apply(y, s, ss, gamma, beta, eps, residual=None, relu=True, running_mean=None, running_var=None,
-             momentum=0.1, training=True):
+             momentum=0.1, training=True, consumed=None):
+    """``consumed``: int32 device counter; when given, the last CTA to have read ``s``/``ss`` zeroes them (they are
+    epilogue-accumulated statistics buffers that the producing conv adds into on its next launch)."""
     yh = nhwc(y)
     out = torch.empty_like(yh)
     c = y.shape[1]
     mean = torch.empty(c, dtype=torch.float32, device=y.device)
     rstd = torch.empty(c, dtype=torch.float32, device=y.device)
     _ext().bn_apply(yh, None if residual is None else nhwc(residual), out, s, ss, gamma, beta, running_mean,
-                    running_var, mean, rstd, eps, momentum, training, relu)
+                    running_var, mean, rstd, eps, momentum, training, relu, consumed)
     return from_nhwc(out), mean, rstd
 
 
@@ -236,6 +252,7 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
 
 import os as _os
 
+EPI_STATS = _os.environ.get("FLUXDIST_EPI_STATS", "1") != "0"  # BN statistics in the conv epilogues
 SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
 _SIDE_PENDING = set()
@@ -389,21 +406,36 @@ class _ConvBNAct(torch.autograd.Function):
         x = x if x.dtype == BF16 else x.to(BF16)
         tc = _tc_ok(w.shape[1], w.shape[0])
         k3 = tc and w.shape[2] == 3 and w.shape[3] == 3 and stride == 1 and pad == 1
+        # BN statistics reduced in the conv epilogue (from the fp32 accumulators): the BN forward is then one
+        # elementwise pass without a grid barrier.  The buffers live in the layer workspace and are re-zeroed by the
+        # apply kernel itself (its last CTA), so the steady state has no memset either.
+        st = None
+        if training and EPI_STATS and bn_ws is not None:
+            c_ = w.shape[0]
+            wf = bn_ws.view(torch.float32)
+            st = (wf[4 + 4 * c_: 4 + 5 * c_], wf[4 + 5 * c_: 4 + 6 * c_])
         if k3 and _halo_fprop_ok(w.shape[1], w.shape[0], x.shape[2]):
-            y = conv3x3_fprop(x, wl)  # halo-tile kernel: one patch load serves all 9 taps
+            y = conv3x3_fprop(x, wl, stats=st if st is not None else False)  # halo-tile kernel: one patch load serves all 9 taps
+            y = y[0] if st is not None else y
         elif tc:
-            y = conv_fprop(x, wl, stride, pad)
+            y = conv_fprop(x, wl, stride, pad, stats=st)
+            y = y[0] if st is not None else y
         elif _is_stem(w.shape, stride, pad, x.shape):
             orig_shape = tuple(x.shape)
             x2 = stem_s2d(x)  # space-to-depth: the 7x7/2 conv becomes a 4x4/1 conv with K = 16 taps x 16 channels
-            y = stem_fprop(x2, wl)
+            y = stem_fprop(x2, wl, stats=st if st is not None else False)
+            y = y[0] if st is not None else y
             x = x2  # saved for the weight gradient instead of the image
             ctx.orig_shape = orig_shape
         else:  # other non-64-multiple channel counts fall back to the library
             y = F.conv2d(x, wl, None, stride, pad)
             y = y.contiguous(memory_format=torch.channels_last)
+            st = None
         fused_bn = training and BN_FUSED and bn_ws is not None
-        if fused_bn:
+        if st is not None:
+            out, mean, rstd = bn_apply(y, st[0], st[1], gamma, beta, eps, residual, relu, rm, rv, momentum, True,
+                                       consumed=bn_ws[2:3])
+        elif fused_bn:
             out, mean, rstd = bn_fwd_fused(y, gamma, beta, eps, bn_ws, residual, relu, rm, rv, momentum)
         else:
             if training:

@@ -78,6 +78,35 @@ def test_conv_fprop(N, H, W, C, K, R, stride, pad):
     assert rel_err(y, ref) < 1e-2
 
 
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", CONV_CASES + [(96, 14, 14, 256, 256, 3, 1, 1), (96, 28, 28, 128, 128, 3, 1, 1)])
+def test_conv_fprop_epilogue_stats(N, H, W, C, K, R, stride, pad):
+    """BN statistics reduced in the implicit-GEMM epilogue (warp transpose-reduce + per-CTA accumulation)."""
+    x, w = _conv_data(N, H, W, C, K, R)
+    y, s, ss = ops.conv_fprop(x, w, stride, pad, stats=True)
+    ref = REF.conv_fprop_ref(x, w, stride, pad)
+    assert rel_err(y, ref) < 1e-2
+    assert rel_err(s, ref.sum(dim=(0, 2, 3))) < 2e-3
+    assert rel_err(ss, (ref * ref).sum(dim=(0, 2, 3))) < 2e-3
+
+
+def test_bn_apply_consumed_counter_rezeroes_stats():
+    """The apply kernel's last CTA clears the epilogue statistics buffers and its own counter."""
+    from fluxdist.ops import native as NV
+
+    C = 128
+    y = cl(torch.randn(8, C, 28, 28, device="cuda").to(BF))
+    s, ss = ops.bn_stats(y)
+    s0, ss0 = s.clone(), ss.clone()
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gamma, beta = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda")
+    out, mean, rstd = NV.bn_apply(y, s, ss, gamma, beta, 1e-5, consumed=cnt)
+    ref, _, _ = NV.bn_apply(y, s0, ss0, gamma, beta, 1e-5)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)
+    assert int(cnt.item()) == 0 and float(s.abs().max()) == 0.0 and float(ss.abs().max()) == 0.0
+    assert float(s0.abs().max()) > 0  # without the counter the buffers are left alone
+
+
 @pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", CONV_CASES)
 def test_conv_dgrad(N, H, W, C, K, R, stride, pad):
     x, w = _conv_data(N, H, W, C, K, R)
