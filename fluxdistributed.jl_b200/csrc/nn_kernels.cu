@@ -2,6 +2,7 @@
 // BatchNorm statistics / apply(+residual,+ReLU) / backward, max-pool, global-average-pool,
 // fused softmax-cross-entropy (loss + dlogits in one pass), uint8 -> bf16 input normalisation.
 // All use 16-byte vector accesses along the channel (innermost) dimension and fp32 arithmetic.
+#include <cstdlib>
 #include "common.cuh"
 #include "nn_kernels.h"
 
@@ -142,31 +143,34 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
   const int C8 = C / 8;
   const long total = M * C8;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
-    const long i1 = i + stride;
-    const bool has1 = i1 < total;
-    V8 y0 = ldg8(y + i * 8), y1, r0, r1;
-    if (has1) y1 = ldg8(y + i1 * 8);
-    if (res) {
-      r0 = ldg8(res + i * 8);
-      if (has1) r1 = ldg8(res + i1 * 8);
+  constexpr int U = 4;  // independent 16-byte loads per tensor in flight per thread
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+    V8 yv[U], rv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        yv[u] = ldg8(y + ii * 8);
+        if (res) rv[u] = ldg8(res + ii * 8);
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !has1) break;
-      const long ii = u ? i1 : i;
-      const int cv = (int)(ii % C8);
-      float f[8], r[8];
-      unpack8(u ? y1 : y0, f);
-      if (res) unpack8(u ? r1 : r0, r);
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        const int ch = (int)(ii % C8) * 8;
+        float f[8], r[8];
+        unpack8(yv[u], f);
+        if (res) unpack8(rv[u], r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float v = f[j] * sc[cv * 8 + j] + sh[cv * 8 + j];
-        if (res) v += r[j];
-        if (relu) v = fmaxf(v, 0.f);
-        f[j] = v;
+        for (int j = 0; j < 8; ++j) {
+          float v = f[j] * sc[ch + j] + sh[ch + j];
+          if (res) v += r[j];
+          if (relu) v = fmaxf(v, 0.f);
+          f[j] = v;
+        }
+        stg8(out + ii * 8, pack8(f));
       }
-      stg8(out + ii * 8, pack8(f));
     }
   }
 }
@@ -453,57 +457,61 @@ bn_fwd_fused_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, const bf16* __restrict__ out,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
                     bf16* __restrict__ dy, bf16* __restrict__ dres, float* __restrict__ accbuf, GridSync gs, long M, int C,
                     int relu) {
+  // Both passes are latency-bound unless many 16-byte loads are in flight per thread: 4 rows x (dout, y[, out]) are
+  // requested before the first use (8-12 outstanding loads per thread, 2 CTAs of 256 threads per SM).
+  constexpr int U = 4;
   extern __shared__ float smem[];
   __shared__ unsigned s_gen0;
   const int C8 = C / 8;
   const int RL = 256 / C8;
   const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
   const bool from_y = relu && (out == nullptr);
+  const bool use_out = relu && !from_y;
   if (threadIdx.x == 0) s_gen0 = *reinterpret_cast<volatile unsigned*>(gs.gen);
-  float acc[2][8];
-  float mu[8], rs[8], gsc[8], gsh[8];
+  float acc[2][8];  // sum dz*(y-mean), sum dz   (the rstd factor is applied after the reduction)
+  float mu[8], gsc[8], gsh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     acc[0][j] = acc[1][j] = 0.f;
     mu[j] = mean[cv * 8 + j];
-    rs[j] = rstd[cv * 8 + j];
-    gsc[j] = gamma[cv * 8 + j] * rs[j];
+    gsc[j] = gamma[cv * 8 + j] * rstd[cv * 8 + j];
     gsh[j] = beta[cv * 8 + j] - mu[j] * gsc[j];
   }
   if (rl < RL) {
     const long per = (M + gridDim.x - 1) / gridDim.x;
     const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
-    for (long r = r0 + rl; r < r1; r += 2L * RL) {
-      const bool has1 = r + RL < r1;
-      const long o0 = r * C + cv * 8, o1 = (r + RL) * C + cv * 8;
-      V8 a0 = ldg8(dout + o0), b0 = ldg8(y + o0), a1, b1, c0, c1;
-      if (has1) {
-        a1 = ldg8(dout + o1);
-        b1 = ldg8(y + o1);
-      }
-      if (relu && !from_y) {
-        c0 = ldg8(out + o0);
-        if (has1) c1 = ldg8(out + o1);
+    for (long r = r0 + rl; r < r1; r += (long)U * RL) {
+      V8 a[U], b[U], c[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long rr = r + (long)u * RL;
+        if (rr < r1) {
+          const long o = rr * C + cv * 8;
+          a[u] = ldg8(dout + o);
+          b[u] = ldg8(y + o);
+          if (use_out) c[u] = ldg8(out + o);
+        }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        if (u == 1 && !has1) break;
-        float d[8], yy[8], o[8];
-        unpack8(u ? a1 : a0, d);
-        unpack8(u ? b1 : b0, yy);
-        if (relu && !from_y) unpack8(u ? c1 : c0, o);
+      for (int u = 0; u < U; ++u) {
+        if (r + (long)u * RL < r1) {
+          float d[8], yy[8], o[8];
+          unpack8(a[u], d);
+          unpack8(b[u], yy);
+          if (use_out) unpack8(c[u], o);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float pre = from_y ? (yy[j] * gsc[j] + gsh[j]) : o[j];
-          const float dz = (relu && !(pre > 0.f)) ? 0.f : d[j];
-          acc[0][j] += dz * (yy[j] - mu[j]) * rs[j];
-          acc[1][j] += dz;
+          for (int j = 0; j < 8; ++j) {
+            const float pre = from_y ? (yy[j] * gsc[j] + gsh[j]) : (use_out ? o[j] : 1.f);
+            const float dz = (relu && !(pre > 0.f)) ? 0.f : d[j];
+            acc[0][j] += dz * (yy[j] - mu[j]);
+            acc[1][j] += dz;
+          }
         }
       }
     }
@@ -519,54 +527,52 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
   float* ka = smem;
   float* kb = smem + C;
   float* kc = smem + 2 * C;
-  float* ksc = smem + 3 * C;
-  float* ksh = smem + 4 * C;
+  float* ksh = smem + 3 * C;
   const float invM = 1.f / (float)M;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const float dg = __ldcg(accum + c), db = __ldcg(accum + C + c);
+    const float g = gamma[c], r_ = rstd[c], m_ = mean[c];
+    const float dg = __ldcg(accum + c) * r_, db = __ldcg(accum + C + c);
     if (blockIdx.x == 0) {
       dgamma[c] = dg;
       dbeta[c] = db;
     }
-    const float g = gamma[c], r_ = rstd[c], m_ = mean[c];
     ka[c] = g * r_;
     kb[c] = -g * r_ * r_ * dg * invM;
     kc[c] = g * r_ * (m_ * r_ * dg * invM - db * invM);
-    ksc[c] = g * r_;
     ksh[c] = beta[c] - m_ * g * r_;
   }
   __syncthreads();
   const long total = M * C8;
   const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += 2 * stride) {
-    const long i1 = i + stride;
-    const bool has1 = i1 < total;
-    V8 a0 = ldg8(dout + i * 8), b0 = ldg8(y + i * 8), a1, b1, c0, c1;
-    if (has1) {
-      a1 = ldg8(dout + i1 * 8);
-      b1 = ldg8(y + i1 * 8);
-    }
-    if (relu && !from_y) {
-      c0 = ldg8(out + i * 8);
-      if (has1) c1 = ldg8(out + i1 * 8);
-    }
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+    V8 a[U], b[U], c[U];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      if (u == 1 && !has1) break;
-      const long ii = u ? i1 : i;
-      const int ch = (int)(ii % C8);
-      float d[8], yy[8], o[8], dz[8];
-      unpack8(u ? a1 : a0, d);
-      unpack8(u ? b1 : b0, yy);
-      if (relu && !from_y) unpack8(u ? c1 : c0, o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float pre = from_y ? (yy[j] * ksc[ch * 8 + j] + ksh[ch * 8 + j]) : o[j];
-        dz[j] = (relu && !(pre > 0.f)) ? 0.f : d[j];
-        d[j] = ka[ch * 8 + j] * dz[j] + kb[ch * 8 + j] * yy[j] + kc[ch * 8 + j];
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        a[u] = ldg8(dout + ii * 8);
+        b[u] = ldg8(y + ii * 8);
+        if (use_out) c[u] = ldg8(out + ii * 8);
       }
-      stg8(dy + ii * 8, pack8(d));
-      if (dres) stg8(dres + ii * 8, pack8(dz));
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        const int ch = (int)(ii % C8) * 8;
+        float d[8], yy[8], o[8], dz[8];
+        unpack8(a[u], d);
+        unpack8(b[u], yy);
+        if (use_out) unpack8(c[u], o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = from_y ? (yy[j] * ka[ch + j] + ksh[ch + j]) : (use_out ? o[j] : 1.f);
+          dz[j] = (relu && !(pre > 0.f)) ? 0.f : d[j];
+          d[j] = ka[ch + j] * dz[j] + kb[ch + j] * yy[j] + kc[ch + j];
+        }
+        stg8(dy + ii * 8, pack8(d));
+        if (dres) stg8(dres + ii * 8, pack8(dz));
+      }
     }
   }
 }
@@ -1039,7 +1045,7 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
 int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s) {
-  int grid = grid_for(M * (C / 8), 256 * 2, 148 * 8);
+  int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
   bn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res), reinterpret_cast<bf16*>(out), sum, sumsq,
       gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu, consumed);
@@ -1200,7 +1206,16 @@ static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
   if (per_sm > 4) per_sm = 4;  // more CTAs = more 16-byte loads in flight (HBM needs ~4.5 MB outstanding)
   // one CTA per ~64 KB of input: small layers must not pay for hundreds of same-address atomics and a wide
   // grid barrier (measured: 592 CTAs cost a fixed ~22 us per launch regardless of tensor size)
-  long want = (M * C * 2 + 65535) / 65536;
+  static long chunk = 0;
+  if (!chunk) {
+    const char* e = getenv("FLUXDIST_BN_CHUNK_KB");  // tuning knob (scripts/bn_bench.py)
+    chunk = (e && atoi(e) > 0) ? 1024L * atoi(e) : 0;
+  }
+  // measured (scripts/bn_bench.py, B200): 64 KB per CTA is best from 9.6 MB up; the 4.8 MB layers (7x7x512) gain 25%
+  // from 32 KB per CTA (twice the CTAs -> half the dependent load rounds)
+  const long bytes = M * C * 2;
+  const long ck = chunk ? chunk : (bytes < (8L << 20) ? 32768 : 65536);
+  long want = (bytes + ck - 1) / ck;
   long cap = (long)sms * per_sm;
   if (want > cap) want = cap;
   if (want < 1) want = 1;

@@ -38,5 +38,6 @@ for hw, C in [(112, 64), (56, 64), (28, 128), (14, 256), (7, 512)]:
     t = timeit(lambda i: (lambda: N.bn_fwd_fused(ys[i], gamma, beta, 1e-5, wss[i], ds[i], True, rm, rv))); r["F_fwd_res_us"] = round(t, 1)
     t = timeit(lambda i: (lambda: N.bn_bwd_fused(ds[i], ys[i], None, mean, rstd, gamma, beta, wss[i], True))); r["F_bwd_us"] = round(t, 1); r["F_bwd_GBs"] = round(5 * V / t * 1e3)
     t = timeit(lambda i: (lambda: N.bn_bwd_fused(ds[i], ys[i], out, mean, rstd, gamma, beta, wss[i], True, want_dres=True))); r["F_bwd_res_us"] = round(t, 1)
+    t = timeit(lambda i: (lambda: N.bn_apply(ys[i], s, ss, gamma, beta, 1e-5, residual=ds[i]))); r["apply_only_res_us"] = round(t, 1)
     t = timeit(lambda i: (lambda: ys[i].add_(ds[i]))); r["torch_add_us"] = round(t, 1); r["torch_add_GBs"] = round(3 * V / t * 1e3)
     print(json.dumps(r), flush=True)
