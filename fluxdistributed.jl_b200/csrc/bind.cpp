@@ -334,6 +334,18 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd", &bn_bwd);
   m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("bn_relu_pool", [](at::Tensor y, at::Tensor out, at::Tensor idx, at::Tensor sum, at::Tensor sumsq, at::Tensor gamma,
+                           at::Tensor beta, c10::optional<at::Tensor> run_mean, c10::optional<at::Tensor> run_var,
+                           c10::optional<at::Tensor> save_mean, c10::optional<at::Tensor> save_rstd, double eps,
+                           double momentum, bool training, c10::optional<at::Tensor> consumed) {
+    want(y, at::kBFloat16, "y");
+    c10::cuda::CUDAGuard guard(y.device());
+    unsigned* cons = consumed.has_value() ? reinterpret_cast<unsigned*>(consumed->data_ptr()) : nullptr;
+    check(fd_bn_relu_pool(y.data_ptr(), out.data_ptr(), idx.data_ptr(), sum.data_ptr<float>(), sumsq.data_ptr<float>(),
+                          gamma.data_ptr<float>(), beta.data_ptr<float>(), optf(run_mean), optf(run_var), optf(save_mean),
+                          optf(save_rstd), (int)y.size(0), (int)y.size(1), (int)y.size(2), (int)y.size(3), (float)eps,
+                          (float)momentum, training ? 1 : 0, cons, cur_stream()), "bn_relu_pool");
+  });
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("maxpool_bwd_idx", [](at::Tensor idx, at::Tensor dout, at::Tensor dx, int k, int stride, int pad) {
     c10::cuda::CUDAGuard guard(dx.device());

@@ -578,6 +578,127 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stem tail in one pass: BatchNorm (statistics from the conv epilogue) + ReLU + 3x3/2/pad-1 max-pool.
+// relu(sc*y+sh) is monotone in y, so the pool runs on the RAW conv output (sign-flipped where sc < 0) with packed
+// bf16x2 max; the arg-max is recovered by SIMD equality against the stored taps; only the pooled value goes through
+// the affine + ReLU.  The 154 MB full-resolution activation of ResNet's stem is never written or re-read.
+// Output: pooled [N,P,Q,C] bf16 and window-relative arg-max bytes (same format as maxpool_fwd_kernel).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_relu_pool3s2_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, uint8_t* __restrict__ idx, float* sum,
+                       float* sumsq, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ save_mean,
+                       float* __restrict__ save_rstd, int N, int H, int W, int C, int P, int Q, float eps, float momentum,
+                       int training, unsigned* consumed) {
+  extern __shared__ float smem[];  // scale[C], shift[C]
+  __shared__ int s_last;
+  float* sc = smem;
+  float* sh = smem + C;
+  const long M = (long)N * H * W;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, var;
+    if (training) {
+      mean = sum[c] * invM;
+      var = fmaxf(sumsq[c] * invM - mean * mean, 0.f);
+    } else {
+      mean = run_mean[c];
+      var = run_var[c];
+    }
+    const float rstd = rsqrtf(var + eps);
+    const float g = gamma[c];
+    sc[c] = g * rstd;
+    sh[c] = beta[c] - mean * g * rstd;
+    if (blockIdx.x == 0) {
+      if (save_mean) save_mean[c] = mean;
+      if (save_rstd) save_rstd[c] = rstd;
+      if (training && run_mean) {
+        const float unbiased = var * ((float)M / fmaxf((float)M - 1.f, 1.f));
+        run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+        run_var[c] = (1.f - momentum) * run_var[c] + momentum * unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  if (consumed) {  // see bn_apply_kernel: the last CTA to have read the statistics clears them
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(consumed, 1u);
+      s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) sum[c] = sumsq[c] = 0.f;
+      if (threadIdx.x == 0) *consumed = 0u;
+    }
+  }
+  const int C8 = C / 8;
+  const long total = (long)N * P * Q * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % C8);
+    long t = i / C8;
+    const int q = (int)(t % Q);
+    t /= Q;
+    const int p = (int)(t % P);
+    const int n = (int)(t / P);
+    // sign-flip mask: channels with a negative scale are pooled by their minimum
+    uint32_t sm[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      sm[e] = (sc[cv * 8 + 2 * e] < 0.f ? 0x8000u : 0u) | (sc[cv * 8 + 2 * e + 1] < 0.f ? 0x80000000u : 0u);
+    uint32_t wv[9][4];
+    bool ok[9];
+    const int h0 = 2 * p - 1, w0 = 2 * q - 1;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int c3 = 0; c3 < 3; ++c3) {
+        const int h = h0 + r, w = w0 + c3;
+        const int tp = r * 3 + c3;
+        ok[tp] = (h >= 0) && (h < H) && (w >= 0) && (w < W);
+        if (ok[tp]) {
+          const V8 v = ldg8(y + (((long)n * H + h) * W + w) * C + cv * 8);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) wv[tp][e] = v.u[e] ^ sm[e];
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) wv[tp][e] = 0xff80ff80u;  // (-inf, -inf)
+        }
+      }
+    __nv_bfloat162 mx[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) mx[e] = *reinterpret_cast<const __nv_bfloat162*>(&wv[0][e]);
+#pragma unroll
+    for (int tp = 1; tp < 9; ++tp)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) mx[e] = __hmax2(mx[e], *reinterpret_cast<const __nv_bfloat162*>(&wv[tp][e]));
+    // first tap (scan order) whose value equals the maximum: walk the taps backwards, overwriting on equality
+    uint32_t am[4] = {0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu, 0x00ff00ffu};
+#pragma unroll
+    for (int tp = 8; tp >= 0; --tp) {
+      if (!ok[tp]) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t eq = __vcmpeq2(wv[tp][e], *reinterpret_cast<const uint32_t*>(&mx[e]));  // 0xFFFF per equal half
+        am[e] = (am[e] & ~eq) | ((uint32_t)tp * 0x00010001u & eq);
+      }
+    }
+    float f[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 v2 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(&mx[e]) ^ sm[e]);
+      f[2 * e] = fmaxf(v2.x * sc[cv * 8 + 2 * e] + sh[cv * 8 + 2 * e], 0.f);
+      f[2 * e + 1] = fmaxf(v2.y * sc[cv * 8 + 2 * e + 1] + sh[cv * 8 + 2 * e + 1], 0.f);
+    }
+    uint2 pk;
+    pk.x = (am[0] & 0xffu) | ((am[0] >> 8) & 0xff00u) | ((am[1] & 0xffu) << 16) | ((am[1] & 0xff0000u) << 8);
+    pk.y = (am[2] & 0xffu) | ((am[2] >> 8) & 0xff00u) | ((am[3] & 0xffu) << 16) | ((am[3] & 0xff0000u) << 8);
+    *reinterpret_cast<uint2*>(idx + i * 8) = pk;
+    stg8(out + i * 8, pack8(f));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Max-pool (k x k, stride, pad) NHWC, 8 channels per thread; backward recomputes the arg-max
 // (first maximum in scan order, matching PyTorch) instead of storing indices.
 // ---------------------------------------------------------------------------------------------
@@ -700,7 +821,10 @@ maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__
     const int p_lo = max(0, (h + pad - k + stride) / stride), p_hi = min(P - 1, (h + pad) / stride);
     const int q_lo = max(0, (w + pad - k + stride) / stride), q_hi = min(Q - 1, (w + pad) / stride);
     if (p_hi - p_lo <= 1 && q_hi - q_lo <= 1) {
-      // common case (k <= 2*stride): at most 2x2 windows -> issue all loads first, then combine
+      // common case (k <= 2*stride): at most 2x2 windows.  All loads are issued first; the arg-max bytes are then
+      // compared 4 at a time (SIMD-in-a-word), the byte mask is widened to bf16 lanes with PRMT and the selected
+      // gradients are summed with packed bf16 adds: ~14 instructions per window instead of ~130 scalar ones (the
+      // kernel was issue-bound, not memory-bound).
       uint2 pk[4];
       V8 dv[4];
       uint32_t pos[4];
@@ -716,17 +840,26 @@ maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__
           dv[u] = ldg8(dout + oi * 8);
         }
       }
+      __nv_bfloat162 acc[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (!ok[u]) continue;
-        float d[8];
-        unpack8(dv[u], d);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t a = ((j < 4 ? pk[u].x : pk[u].y) >> ((j & 3) * 8)) & 255u;
-          if (a == pos[u]) g[j] += d[j];
-        }
+        const uint32_t rep = pos[u] * 0x01010101u;
+        const uint32_t m_lo = __vcmpeq4(pk[u].x, rep), m_hi = __vcmpeq4(pk[u].y, rep);  // 0xFF per matching channel
+        const uint32_t w0 = dv[u].u[0] & __byte_perm(m_lo, 0, 0x1100), w1 = dv[u].u[1] & __byte_perm(m_lo, 0, 0x3322);
+        const uint32_t w2 = dv[u].u[2] & __byte_perm(m_hi, 0, 0x1100), w3 = dv[u].u[3] & __byte_perm(m_hi, 0, 0x3322);
+        acc[0] = __hadd2(acc[0], *reinterpret_cast<const __nv_bfloat162*>(&w0));
+        acc[1] = __hadd2(acc[1], *reinterpret_cast<const __nv_bfloat162*>(&w1));
+        acc[2] = __hadd2(acc[2], *reinterpret_cast<const __nv_bfloat162*>(&w2));
+        acc[3] = __hadd2(acc[3], *reinterpret_cast<const __nv_bfloat162*>(&w3));
       }
+      V8 o;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o.u[e] = *reinterpret_cast<const uint32_t*>(&acc[e]);
+      stg8(dx + i * 8, o);
+      continue;
     } else {
       for (int p = p_lo; p <= p_hi; ++p)
         for (int q = q_lo; q <= q_hi; ++q) {
@@ -1070,6 +1203,19 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
   bn_bwd_apply_kernel<<<grid2, 256, 5 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
       rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), M, C, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_bn_relu_pool(const void* y, void* out, void* idx, float* sum, float* sumsq, const float* gamma, const float* beta,
+                    float* run_mean, float* run_var, float* save_mean, float* save_rstd, int N, int H, int W, int C,
+                    float eps, float momentum, int training, unsigned* consumed, cudaStream_t s) {
+  if (C % 8) { fd_set_error("bn_relu_pool: C must be a multiple of 8", __FILE__, __LINE__); return -1; }
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 8);
+  bn_relu_pool3s2_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
+      reinterpret_cast<const bf16*>(y), reinterpret_cast<bf16*>(out), reinterpret_cast<uint8_t*>(idx), sum, sumsq, gamma,
+      beta, run_mean, run_var, save_mean, save_rstd, N, H, W, C, P, Q, eps, momentum, training, consumed);
   FD_LAUNCH_OK();
   return 0;
 }

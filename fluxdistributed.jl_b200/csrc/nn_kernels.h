@@ -7,6 +7,10 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
 int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s);
+// BN (+ReLU) + 3x3/2/pad-1 max-pool of y[N,H,W,C] in one pass -> out[N,P,Q,C], idx (window-relative arg-max bytes)
+int fd_bn_relu_pool(const void* y, void* out, void* idx, float* sum, float* sumsq, const float* gamma, const float* beta,
+                    float* run_mean, float* run_var, float* save_mean, float* save_rstd, int N, int H, int W, int C,
+                    float eps, float momentum, int training, unsigned* consumed, cudaStream_t s);
 int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, long M, int C,
               int relu, cudaStream_t s);

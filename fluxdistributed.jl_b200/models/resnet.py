@@ -79,7 +79,10 @@ class ResNet(nn.Module):
         self.nclasses = nclasses
 
     def features(self, x):
-        x = self.pool(self.stem(x))
+        if (self.pool.k, self.pool.stride, self.pool.padding) == (3, 2, 1):
+            x = self.stem(x, pool=True)  # BN + ReLU + max-pool in one pass on the native path (ops.bn_relu_pool)
+        else:
+            x = self.pool(self.stem(x))
         return self.layer4(self.layer3(self.layer2(self.layer1(x))))
 
     def forward(self, x):

@@ -89,7 +89,7 @@ class ConvBN(nn.Module):
             nn.init.zeros_(self.bn.weight)
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, add_link=None, res_link=None,
-                park_link=None) -> torch.Tensor:
+                park_link=None, pool: bool = False) -> torch.Tensor:
         if _use_native(x):
             from ..ops import conv_bn_act
             from ..ops.native import bn_workspace
@@ -103,7 +103,7 @@ class ConvBN(nn.Module):
                                getattr(self.conv.weight, "_lowp", None),
                                (getattr(self.conv.weight, "_gradbuf", None), getattr(self.bn.weight, "_gradbuf", None),
                                 getattr(self.bn.bias, "_gradbuf", None)), ws,
-                               add_link, res_link, park_link)
+                               add_link, res_link, park_link, pool)
         w = self.conv.weight
         if x.dtype != w.dtype:
             w = w.to(x.dtype)
@@ -112,7 +112,8 @@ class ConvBN(nn.Module):
                          self.training, self.bn.momentum, self.bn.eps)
         if residual is not None:
             y = y + residual
-        return F.relu(y) if self.relu else y
+        y = F.relu(y) if self.relu else y
+        return F.max_pool2d(y, 3, 2, 1) if pool else y
 
     def extra_repr(self):
         return f"{self.cin}, {self.cout}, k={self.k}, s={self.stride}, p={self.padding}, relu={self.relu}"

@@ -236,6 +236,22 @@ def bn_apply(y, s, ss, gamma, beta, eps, residual=None, relu=True, running_mean=
     return from_nhwc(out), mean, rstd
 
 
+def bn_relu_pool(y, s, ss, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1, training=True,
+                 consumed=None):
+    """BN + ReLU + 3x3/stride-2/pad-1 max-pool in one pass over the raw conv output ``y`` (the stem tail):
+    returns (pooled, argmax bytes, mean, rstd).  The full-resolution BN output is never materialised."""
+    yh = nhwc(y)
+    n, h, w, c = yh.shape
+    p, q = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    out = torch.empty(n, p, q, c, dtype=BF16, device=y.device)
+    idx = torch.empty(n, p, q, c, dtype=torch.uint8, device=y.device)
+    mean = torch.empty(c, dtype=torch.float32, device=y.device)
+    rstd = torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_relu_pool(yh, out, idx, s, ss, gamma, beta, running_mean, running_var, mean, rstd, eps, momentum, training,
+                        consumed)
+    return from_nhwc(out), idx, mean, rstd
+
+
 def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=None, dbeta=None, beta=None):
     yh = nhwc(y)
     c = y.shape[1]
@@ -390,7 +406,8 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                w_gradbuf, bn_ws=None, add_link=None, res_link=None, park_link=None):
+                w_gradbuf, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False):
+        # pool: fuse a 3x3/2/pad-1 max-pool behind BN+ReLU (ResNet stem): see bn_relu_pool
         # park_link: given to a 1x1/stride-2 projection shortcut whose input is also read by a stride-2 3x3 conv that
         # got the same dict as add_link.  The projection parks its data gradient as a COMPACT [N,H/2,W/2,C] tensor (a
         # plain GEMM) and the 3x3's parity-decomposed dgrad sums it into its (even, even) class.
@@ -432,7 +449,19 @@ class _ConvBNAct(torch.autograd.Function):
             y = y.contiguous(memory_format=torch.channels_last)
             st = None
         fused_bn = training and BN_FUSED and bn_ws is not None
-        if st is not None:
+        ctx.pool_idx = None
+        if pool:
+            assert relu and residual is None, "fused pool needs a plain BN+ReLU layer"
+            if st is not None:
+                out, ctx.pool_idx, mean, rstd = bn_relu_pool(y, st[0], st[1], gamma, beta, eps, rm, rv, momentum, True,
+                                                             consumed=bn_ws[2:3])
+            else:
+                if training:
+                    s, ss = bn_stats(y)
+                else:
+                    s = ss = gamma  # unused
+                out, ctx.pool_idx, mean, rstd = bn_relu_pool(y, s, ss, gamma, beta, eps, rm, rv, momentum, training)
+        elif st is not None:
             out, mean, rstd = bn_apply(y, st[0], st[1], gamma, beta, eps, residual, relu, rm, rv, momentum, True,
                                        consumed=bn_ws[2:3])
         elif fused_bn:
@@ -456,6 +485,11 @@ class _ConvBNAct(torch.autograd.Function):
         x, wl, y, out, mean, rstd, gamma, beta = ctx.saved_tensors
         relu, stride, pad, has_res, tc, w_shape, x_shape, k3, stem = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
+        if ctx.pool_idx is not None:  # route the pooled gradient back to full resolution (gather, no atomics)
+            n_, c_, h_, w_ = y.shape
+            dfull = torch.empty(n_, h_, w_, c_, dtype=BF16, device=y.device)
+            _ext().maxpool_bwd_idx(ctx.pool_idx, nhwc(dout), dfull, 3, 2, 1)
+            dout = from_nhwc(dfull)
         if ctx.bn_ws is not None:
             dy, dgamma, dbeta, dres = bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ctx.bn_ws, relu,
                                                    want_dres=has_res, dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
@@ -508,13 +542,13 @@ class _ConvBNAct(torch.autograd.Function):
         # when the gradient already landed in the arena, autograd must not add it a second time
         dw = None if ctx.w_gradbuf is not None else gw
         return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
-                None, None, None, None, None, None)
+                None, None, None, None, None, None, None)
 
 
 def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
-                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None, park_link=None):
+                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False):
     return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                            w_gradbuf, bn_ws, add_link, res_link, park_link)
+                            w_gradbuf, bn_ws, add_link, res_link, park_link, pool)
 
 
 # --------------------------------------------------------------------------- autograd: max-pool, GAP + FC

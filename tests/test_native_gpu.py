@@ -89,6 +89,39 @@ def test_conv_fprop_epilogue_stats(N, H, W, C, K, R, stride, pad):
     assert rel_err(ss, (ref * ref).sum(dim=(0, 2, 3))) < 2e-3
 
 
+@pytest.mark.parametrize("N,H,W,C", [(4, 112, 112, 64), (3, 30, 22, 64), (2, 17, 15, 128)])
+def test_bn_relu_pool_fused(N, H, W, C):
+    """BN + ReLU + 3x3/2 max-pool in one pass == the three separate ops (values and gradient routing), including
+    channels with a negative scale (pooled through their minimum)."""
+    import torch.nn.functional as F
+    from fluxdist.ops import native as NV
+
+    torch.manual_seed(1)
+    y = cl(torch.randn(N, C, H, W, device="cuda").to(BF))
+    gamma = torch.randn(C, device="cuda")  # both signs
+    beta = torch.randn(C, device="cuda") * 0.3
+    s, ss = ops.bn_stats(y)
+    pooled, idx, mean, rstd = NV.bn_relu_pool(y, s.clone(), ss.clone(), gamma, beta, 1e-5)
+    yf = y.float()
+    mu = yf.mean(dim=(0, 2, 3)); var = yf.var(dim=(0, 2, 3), unbiased=False)
+    act = torch.relu((yf - mu[None, :, None, None]) / torch.sqrt(var + 1e-5)[None, :, None, None]
+                     * gamma[None, :, None, None] + beta[None, :, None, None]).requires_grad_(True)
+    ref = F.max_pool2d(act, 3, 2, 1)
+    assert pooled.shape == ref.shape
+    assert rel_err(pooled, ref) < 1e-2
+    assert rel_err(mean, mu) < 1e-3
+    # gradient routing: scatter a random pooled gradient back through the recorded arg-max
+    g = cl(torch.randn_like(ref).to(BF))
+    dfull = torch.empty(N, H, W, C, dtype=BF, device="cuda")
+    ops.extension().maxpool_bwd_idx(idx, g.permute(0, 2, 3, 1), dfull, 3, 2, 1)
+    ref.backward(g.float())
+    # positions can differ only where the pooled activation is 0 (ties among clamped values): mask them out, as the
+    # ReLU mask of the BN backward does
+    live = (act.detach() > 0)
+    got = dfull.permute(0, 3, 1, 2).float() * live
+    assert rel_err(got, act.grad * live) < 2e-2
+
+
 def test_bn_apply_consumed_counter_rezeroes_stats():
     """The apply kernel's last CTA clears the epilogue statistics buffers and its own counter."""
     from fluxdist.ops import native as NV
