@@ -107,12 +107,28 @@ void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad, c
                       (int)x.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
         "conv_fprop");
 }
-void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::optional<at::Tensor> add) {
+// bn_epi (optional): [y, out-or-empty, mean, rstd, gamma, beta, s0, s1] of the BN layer whose output gradient is produced
+void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::optional<at::Tensor> add,
+                c10::optional<std::vector<at::Tensor>> bn_epi) {
   want(dy, at::kBFloat16, "dy");
   want(w, at::kBFloat16, "w");
   want(dx, at::kBFloat16, "dx");
   c10::cuda::CUDAGuard guard(dy.device());
-  check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+  FdBnEpilogue bz{};
+  const FdBnEpilogue* bzp = nullptr;
+  if (bn_epi.has_value()) {
+    const auto& v = *bn_epi;
+    TORCH_CHECK(v.size() == 8, "bn_epi: 8 tensors expected");
+    want(v[0], at::kBFloat16, "bn_epi.y");
+    TORCH_CHECK(v[0].numel() == dx.numel(), "bn_epi.y must have the shape of dx");
+    bz.y = v[0].data_ptr();
+    bz.out = v[1].numel() ? v[1].data_ptr() : nullptr;
+    bz.mean = v[2].data_ptr<float>(); bz.rstd = v[3].data_ptr<float>();
+    bz.gamma = v[4].data_ptr<float>(); bz.beta = v[5].data_ptr<float>();
+    bz.s0 = v[6].data_ptr<float>(); bz.s1 = v[7].data_ptr<float>();
+    bzp = &bz;
+  }
+  check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), bzp, (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
                       (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
         "conv_dgrad");
 }
@@ -334,6 +350,17 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_apply", &bn_apply);
   m.def("bn_bwd", &bn_bwd);
   m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("bn_bwd_apply", [](at::Tensor dz, at::Tensor y, at::Tensor mean, at::Tensor rstd, at::Tensor gamma, at::Tensor s0,
+                           at::Tensor s1, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy, c10::optional<at::Tensor> consumed) {
+    want(dz, at::kBFloat16, "dz");
+    want(y, at::kBFloat16, "y");
+    c10::cuda::CUDAGuard guard(y.device());
+    const int C = (int)gamma.numel();
+    unsigned* cons = consumed.has_value() ? reinterpret_cast<unsigned*>(consumed->data_ptr()) : nullptr;
+    check(fd_bn_bwd_apply(dz.data_ptr(), y.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), gamma.data_ptr<float>(),
+                          s0.data_ptr<float>(), s1.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
+                          dy.data_ptr(), y.numel() / C, C, cons, cur_stream()), "bn_bwd_apply");
+  });
   m.def("bn_relu_pool", [](at::Tensor y, at::Tensor out, at::Tensor idx, at::Tensor sum, at::Tensor sumsq, at::Tensor gamma,
                            at::Tensor beta, c10::optional<at::Tensor> run_mean, c10::optional<at::Tensor> run_var,
                            c10::optional<at::Tensor> save_mean, c10::optional<at::Tensor> save_rstd, double eps,

@@ -9,8 +9,15 @@ int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int o
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K, int R, int S, int stride,
                   int pad, cudaStream_t s);
-int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
-                  int pad, cudaStream_t s);
+// "dz epilogue" of the stride-1 data gradient (see KParams::bz_* in igemm_sm100.cu): BN layer whose output gradient this is
+struct FdBnEpilogue {
+  const void* y;      // raw conv output of that layer [N,H,W,C] bf16
+  const void* out;    // its post-residual activation (mask source) or null (mask recomputed from y)
+  const float *mean, *rstd, *gamma, *beta;
+  float *s0, *s1;     // accumulators (zeroed by the consumer): sum dz*(y-mean), sum dz
+};
+int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, const FdBnEpilogue* bz, int N, int H, int W, int C,
+                  int K, int R, int S, int pad, cudaStream_t s);
 // stride-2 data gradient without a zero-upsampled tensor: 4 output-parity classes, each a stride-1 correlation with the
 // taps that reach it (R,S <= 3; H,W even).  `add_compact` ([N,H/2,W/2,C], optional) is summed into the (even,even) class:
 // it carries the data gradient of a parallel 1x1/stride-2 projection.  Parity classes no tap reaches are NOT written.

@@ -69,6 +69,19 @@ struct KParams {
   // fprop: per-output-channel sum / sum of squares of the fp32 accumulators, added atomically (fused BN statistics)
   float* st_sum;
   float* st_sq;
+  // dgrad (stride 1): "dz epilogue".  The tensor this dgrad produces is the gradient w.r.t. the OUTPUT of a BN(+ReLU)
+  // layer.  With bz_y set the epilogue applies that layer's ReLU mask, stores dz = mask * dx instead of dx and reduces
+  // sum(dz) and sum(dz * (y - mean)) per channel, i.e. the whole first pass of the BN backward; what remains of it is
+  // one elementwise pass (bn_bwd_apply).  bz_out != null: mask from the layer's post-residual activation (out > 0),
+  // else recomputed from y.
+  const void* bz_y;
+  const void* bz_out;
+  const float* bz_mean;
+  const float* bz_rstd;
+  const float* bz_gamma;
+  const float* bz_beta;
+  float* bz_s0;  // += sum dz * (y - mean)
+  float* bz_s1;  // += sum dz
 };
 
 // 32x32 transpose-reduce across a warp: lane l holds v[0..31] (row l of a 32-row block); on return v[0] of lane l is the
@@ -101,7 +114,7 @@ struct Cfg {
 // they need the same B (filter) tile: each CTA fetches HALF of it and the copy engine multicasts it into both CTAs'
 // shared memory (.multicast::cluster), halving the L2 traffic of the operand that every m-tile re-reads.  Shared-memory
 // slots are released cluster-wide (tcgen05.commit ... .multicast::cluster on both CTAs' empty barriers).
-template <int BN, int MODE, bool MC = false>
+template <int BN, int MODE, bool MC = false, bool BZ = false>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams P) {
   using C = Cfg<BN, MODE>;
@@ -305,7 +318,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    const bool do_stats = (MODE == MODE_FPROP) && P.st_sum != nullptr;
+    constexpr bool bz = BZ && (MODE == MODE_DGRAD);  // dz epilogue compiled into its own instantiation
+    const bool do_stats = ((MODE == MODE_FPROP) && P.st_sum != nullptr) || bz;
+    float* const red0 = bz ? P.bz_s1 : P.st_sum;  // st_s: sum x (fprop) / sum dz (dgrad)
+    float* const red1 = bz ? P.bz_s0 : P.st_sq;   // st_q: sum x^2 (fprop) / sum dz*(y-mean) (dgrad)
+    // per epilogue warp: mean | gamma*rstd | shift of the tile's channels (static shared: plain LDS, no generic loads)
+    __shared__ float bnpar_all[bz ? 4 * 3 * BN : 4];
+    float* const bnpar = bnpar_all + (bz ? (warp - 2) * 3 * BN : 0);
     float st_s[BN / 32], st_q[BN / 32];  // this lane's channel (c0 + lane) of each 32-column chunk, over this CTA's tiles
 #pragma unroll
     for (int i = 0; i < BN / 32; ++i) st_s[i] = st_q[i] = 0.f;
@@ -314,8 +333,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       if (st_nt >= 0) {
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i) {
-          atomicAdd(P.st_sum + st_nt * BN + i * 32 + lane, st_s[i]);
-          atomicAdd(P.st_sq + st_nt * BN + i * 32 + lane, st_q[i]);
+          atomicAdd(red0 + st_nt * BN + i * 32 + lane, st_s[i]);
+          atomicAdd(red1 + st_nt * BN + i * 32 + lane, st_q[i]);
           st_s[i] = st_q[i] = 0.f;
         }
       }
@@ -328,10 +347,29 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       if (do_stats && nt != st_nt) {
         flush_stats();
         st_nt = nt;
+        if (bz) {  // this warp's copy of the BN coefficients of the tile's channels
+          __syncwarp();
+          for (int c = lane; c < BN; c += 32) {
+            const int ch = nt * BN + c;
+            const float mu = P.bz_mean[ch], g = P.bz_gamma[ch] * P.bz_rstd[ch];
+            bnpar[c] = mu;
+            bnpar[BN + c] = g;
+            bnpar[2 * BN + c] = P.bz_beta[ch] - mu * g;
+          }
+          __syncwarp();
+        }
+      }
+      const int row = m0 + quad * 32 + lane;
+      // dz epilogue: the BN layer's y tile is requested BEFORE waiting for the accumulator, so its global-memory
+      // latency overlaps the MMAs of this tile instead of serialising with the TMEM reads
+      uint4 ypre[bz ? BN / 8 : 1];
+      if (bz) {
+        const bf16* yrow = reinterpret_cast<const bf16*>(P.bz_y) + (long)row * P.ldo + nt * BN;
+#pragma unroll
+        for (int j = 0; j < BN / 8; ++j) ypre[j] = (row < P.M) ? *reinterpret_cast<const uint4*>(yrow + j * 8) : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
       bool has_k = true;
       if (MODE == MODE_WGRAD) {
         int b0 = (int)(((long)P.kb_total * split) / P.splits);
@@ -343,7 +381,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
-        if (do_stats) {  // rows past M are TMA zero-fill: they add nothing
+        bool added = false;
+        if (bz) {
+          float f[32], q[32];
+          const bool live = row < P.M;
+          const long off = (long)row * P.ldo + nt * BN + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 yv = ypre[(c0 + j) / 8], av = make_uint4(0, 0, 0, 0), ov = av;
+            if (live) {
+              if (P.add) av = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.add) + off + j);
+              if (P.bz_out) ov = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_out) + off + j);
+            }
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, aw[4] = {av.x, av.y, av.z, av.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 y2 = unpack_bf16x2(yw[e]), a2 = unpack_bf16x2(aw[e]), o2 = unpack_bf16x2(ow[e]);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int jj = j + 2 * e + h2;
+                const float yy = h2 ? y2.y : y2.x;
+                const float x = __uint_as_float(v[jj]) + (h2 ? a2.y : a2.x);
+                const float pre = P.bz_out ? (h2 ? o2.y : o2.x) : (yy * bnpar[BN + c0 + jj] + bnpar[2 * BN + c0 + jj]);
+                const float dz = (live && pre > 0.f) ? x : 0.f;
+                f[jj] = dz;
+                q[jj] = dz * (yy - bnpar[c0 + jj]);
+                v[jj] = __float_as_uint(dz);
+              }
+            }
+          }
+          st_s[c0 / 32] += warp_column_sums(f, lane);
+          st_q[c0 / 32] += warp_column_sums(q, lane);
+          added = true;  // `add` is already inside v
+        } else if (do_stats) {  // rows past M are TMA zero-fill: they add nothing
           float f[32], q[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -383,7 +453,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               }
             } else {
               long orow = row;  // row of the output matrix this accumulator row lands in
-              bool use_add = P.add != nullptr;
+              bool use_add = P.add != nullptr && !added;
               if (MODE == MODE_DGRAD_S2) {
                 const int n_ = row / P.PQ, r2 = row - n_ * P.PQ;
                 const int i_ = r2 / P.Q, j_ = r2 - i_ * P.Q;
@@ -511,20 +581,20 @@ int make_map_im2col(CUtensorMap* m, const void* base, int N, int H, int W, int C
   return 0;
 }
 
-template <int BN, int MODE>
+template <int BN, int MODE, bool BZ = false>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStream_t s) {
   using C = Cfg<BN, MODE>;
   static bool attr_set[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 15]) {
-    FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE, false, BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set[dev & 15] = true;
   }
   int tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
   if (grid < 1) grid = 1;
-  igemm_kernel<BN, MODE><<<grid, kThreads, C::SMEM_BYTES, s>>>(a, b, p);
+  igemm_kernel<BN, MODE, false, BZ><<<grid, kThreads, C::SMEM_BYTES, s>>>(a, b, p);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -653,8 +723,8 @@ int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sums
   return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
 }
 
-int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K, int R, int S,
-                  int pad, cudaStream_t s) {
+int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, const FdBnEpilogue* bz, int N, int H, int W, int C,
+                  int K, int R, int S, int pad, cudaStream_t s) {
   // stride-1 data gradient: dx[N,H,W,C] from dy[N,P,Q,K]; P = H + 2pad - R + 1
   if (ensure_driver()) return -1;
   if (C % 64 || K % 64) {
@@ -679,6 +749,11 @@ int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, int 
   p.PQ = H * W; p.Q = W; p.stride = 1; p.lower_w = pad - (S - 1); p.lower_h = pad - (R - 1);
   p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
   p.out = dx; p.ldo = C; p.out_fp32 = 0; p.add = add;
+  if (bz) {
+    p.bz_y = bz->y; p.bz_out = bz->out; p.bz_mean = bz->mean; p.bz_rstd = bz->rstd; p.bz_gamma = bz->gamma;
+    p.bz_beta = bz->beta; p.bz_s0 = bz->s0; p.bz_s1 = bz->s1;
+    return bn == 64 ? launch<64, MODE_DGRAD, true>(ma, mb, p, s) : launch<128, MODE_DGRAD, true>(ma, mb, p, s);
+  }
   return bn == 64 ? launch<64, MODE_DGRAD>(ma, mb, p, s) : launch<128, MODE_DGRAD>(ma, mb, p, s);
 }
 

@@ -578,6 +578,77 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Second (and only remaining) pass of the BN backward when the producer of the output gradient already applied the
+// ReLU mask and reduced sum(dz), sum(dz*(y-mean)) in its epilogue (igemm "dz epilogue"):
+//   dy = g*rstd * dz - g*rstd^2*dgamma/M * (y-mean)... folded into  ka*dz + kb*y + kc.
+// No grid barrier, no second read of the inputs.  The last CTA to have read the accumulators clears them.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, const float* __restrict__ mean,
+                    const float* __restrict__ rstd, const float* __restrict__ gamma, float* s0, float* s1,
+                    float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dy, long M, int C,
+                    unsigned* consumed) {
+  extern __shared__ float smem[];
+  __shared__ int s_last;
+  float* ka = smem;
+  float* kb = smem + C;
+  float* kc = smem + 2 * C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g = gamma[c], r_ = rstd[c], m_ = mean[c];
+    const float dg = s0[c] * r_, db = s1[c];
+    if (blockIdx.x == 0) {
+      dgamma[c] = dg;
+      dbeta[c] = db;
+    }
+    ka[c] = g * r_;
+    kb[c] = -g * r_ * r_ * dg * invM;
+    kc[c] = g * r_ * (m_ * r_ * dg * invM - db * invM);
+  }
+  __syncthreads();
+  if (consumed) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      const unsigned prev = atomicAdd(consumed, 1u);
+      s_last = (prev == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      for (int c = threadIdx.x; c < C; c += blockDim.x) s0[c] = s1[c] = 0.f;
+      if (threadIdx.x == 0) *consumed = 0u;
+    }
+  }
+  constexpr int U = 4;
+  const int C8 = C / 8;
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+    V8 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        a[u] = ldg8(dz + ii * 8);
+        b[u] = ldg8(y + ii * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        const int ch = (int)(ii % C8) * 8;
+        float d[8], yy[8];
+        unpack8(a[u], d);
+        unpack8(b[u], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d[j] = ka[ch + j] * d[j] + kb[ch + j] * yy[j] + kc[ch + j];
+        stg8(dy + ii * 8, pack8(d));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stem tail in one pass: BatchNorm (statistics from the conv epilogue) + ReLU + 3x3/2/pad-1 max-pool.
 // relu(sc*y+sh) is monotone in y, so the pool runs on the RAW conv output (sign-flipped where sc < 0) with packed
 // bf16x2 max; the arg-max is recovered by SIMD equality against the stored taps; only the pooled value goes through
@@ -1203,6 +1274,17 @@ int fd_bn_bwd(const void* dout, const void* y, const void* out, const float* mea
   bn_bwd_apply_kernel<<<grid2, 256, 5 * C * sizeof(float), s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
       rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), M, C, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+int fd_bn_bwd_apply(const void* dz, const void* y, const float* mean, const float* rstd, const float* gamma, float* s0,
+                    float* s1, float* dgamma, float* dbeta, void* dy, long M, int C, unsigned* consumed, cudaStream_t s) {
+  if (C % 8) { fd_set_error("bn_bwd_apply: C must be a multiple of 8", __FILE__, __LINE__); return -1; }
+  int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
+  bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), s>>>(
+      reinterpret_cast<const bf16*>(dz), reinterpret_cast<const bf16*>(y), mean, rstd, gamma, s0, s1, dgamma, dbeta,
+      reinterpret_cast<bf16*>(dy), M, C, consumed);
   FD_LAUNCH_OK();
   return 0;
 }

@@ -7,6 +7,10 @@ int fd_bn_stats(const void* y, float* sum, float* sumsq, long M, int C, cudaStre
 int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* sumsq, const float* gamma,
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s);
+// single-pass BN backward for a pre-masked gradient dz with sums s0 = sum dz*(y-mean), s1 = sum dz already reduced by the
+// producer (igemm dz epilogue); clears s0/s1 through `consumed`
+int fd_bn_bwd_apply(const void* dz, const void* y, const float* mean, const float* rstd, const float* gamma, float* s0,
+                    float* s1, float* dgamma, float* dbeta, void* dy, long M, int C, unsigned* consumed, cudaStream_t s);
 // BN (+ReLU) + 3x3/2/pad-1 max-pool of y[N,H,W,C] in one pass -> out[N,P,Q,C], idx (window-relative arg-max bytes)
 int fd_bn_relu_pool(const void* y, void* out, void* idx, float* sum, float* sumsq, const float* gamma, const float* beta,
                     float* run_mean, float* run_var, float* save_mean, float* save_rstd, int N, int H, int W, int C,
@@ -37,8 +41,9 @@ int fd_stem_w_s2d(const void* w, void* w2, int K, cudaStream_t s);
 int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s);
 #define FD_BN_MAX_GRID 296
 // workspace bytes for the single-launch BN kernels with at most `C` channels
-// [barrier counter, generation, stats-consumed counter, pad] + 2 x [2][C] barrier-kernel accumulators + [2][C] epilogue statistics
-inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)6 * C * sizeof(float); }
+// [barrier counter, generation, fwd-stats-consumed counter, bwd-sums-consumed counter] + 2 x [2][C] barrier-kernel
+// accumulators + [2][C] forward epilogue statistics + [2][C] backward epilogue sums
+inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)8 * C * sizeof(float); }
 int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,
                     float momentum, int relu, cudaStream_t s);

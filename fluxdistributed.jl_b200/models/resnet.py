@@ -29,16 +29,18 @@ class BasicBlock(nn.Module):
         if self.downsample is None and self.conv1.stride == 1 and x.is_cuda and x.dtype == torch.bfloat16 \
                 and torch.is_grad_enabled() and self.conv1.cin % 64 == 0:
             # identity skip: the residual gradient is summed into conv1's dgrad epilogue (see ops/native.py)
-            link = {}
-            return self.conv2(self.conv1(x, add_link=link), residual=x, res_link=link)
+            link, mid = {}, {}
+            # `mid`: conv1's output is consumed by conv2 only, so conv2's dgrad epilogue may do the reduction pass of
+            # conv1's BN backward (mask + per-channel sums) and hand over the masked gradient
+            return self.conv2(self.conv1(x, add_link=link, own_link=mid), residual=x, res_link=link, src_link=mid)
         if self.downsample is not None and self.conv1.stride == 2 and self.downsample.stride == 2 and x.is_cuda \
                 and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and self.conv1.cin % 64 == 0 \
                 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
             # projection skip: the 1x1/2 conv parks its (compact) data gradient and the 3x3/2 conv's parity-decomposed
             # dgrad adds it in its epilogue; conv1 runs first so that autograd schedules the projection's backward first
-            link = {"expect_compact": True}
-            h = self.conv1(x, add_link=link)
-            return self.conv2(h, residual=self.downsample(x, park_link=link))
+            link, mid = {"expect_compact": True}, {}
+            h = self.conv1(x, add_link=link, own_link=mid)
+            return self.conv2(h, residual=self.downsample(x, park_link=link), src_link=mid)
         idn = x if self.downsample is None else self.downsample(x)
         return self.conv2(self.conv1(x), residual=idn)
 

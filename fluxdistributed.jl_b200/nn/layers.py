@@ -89,7 +89,7 @@ class ConvBN(nn.Module):
             nn.init.zeros_(self.bn.weight)
 
     def forward(self, x: torch.Tensor, residual: Optional[torch.Tensor] = None, add_link=None, res_link=None,
-                park_link=None, pool: bool = False) -> torch.Tensor:
+                park_link=None, pool: bool = False, own_link=None, src_link=None) -> torch.Tensor:
         if _use_native(x):
             from ..ops import conv_bn_act
             from ..ops.native import bn_workspace
@@ -103,7 +103,7 @@ class ConvBN(nn.Module):
                                getattr(self.conv.weight, "_lowp", None),
                                (getattr(self.conv.weight, "_gradbuf", None), getattr(self.bn.weight, "_gradbuf", None),
                                 getattr(self.bn.bias, "_gradbuf", None)), ws,
-                               add_link, res_link, park_link, pool)
+                               add_link, res_link, park_link, pool, own_link, src_link)
         w = self.conv.weight
         if x.dtype != w.dtype:
             w = w.to(x.dtype)

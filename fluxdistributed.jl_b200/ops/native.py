@@ -169,12 +169,16 @@ def _s2_native_ok(h: int, ww: int, r: int, s: int, pad: int) -> bool:
 
 
 def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int,
-               add: Optional[torch.Tensor] = None, add_compact: Optional[torch.Tensor] = None) -> torch.Tensor:
+               add: Optional[torch.Tensor] = None, add_compact: Optional[torch.Tensor] = None,
+               bn_epi=None) -> torch.Tensor:
     """Data gradient.  Stride 1 runs the tcgen05 dgrad directly.  Stride 2 (1x1 / 3x3 filters, even images) runs the
     parity-decomposed kernel: each (h%2, w%2) class of dx is a stride-1 correlation of dy with the taps that reach it,
     so neither a zero-upsampled copy of dy nor multiplications by its zeros exist.  ``add_compact`` ([N,C,H/2,W/2]) is
     summed into the (even, even) class: the data gradient of a parallel 1x1/stride-2 projection (ResNet downsample).
-    Other strided geometries zero-upsample ``dy`` and reuse the stride-1 kernel."""
+    Other strided geometries zero-upsample ``dy`` and reuse the stride-1 kernel.
+    ``bn_epi`` (stride 1 only) = ``(y, out|None, mean, rstd, gamma, beta, s0, s1)`` of the BN(+ReLU) layer whose output
+    gradient this is: the epilogue then stores the ReLU-masked gradient dz and adds sum dz*(y-mean) / sum dz into
+    ``s0`` / ``s1`` (the reduction pass of that layer's backward; finish with :func:`bn_bwd_apply`)."""
     n, c, h, ww = x_shape
     dyh, wk = nhwc(dy), krsc(w)
     k, r, s, _ = wk.shape
@@ -193,7 +197,13 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int
         _ext().upsample_zero(dyh, up, stride)
         dyh = up
     dx = torch.empty(n, h, ww, c, dtype=BF16, device=dy.device)
-    _ext().conv_dgrad(dyh, wk, dx, pad, None if add is None else nhwc(add))
+    epi = None
+    if bn_epi is not None:
+        assert stride == 1, "the dz epilogue is implemented for stride-1 dgrad"
+        y_, out_, mean_, rstd_, gamma_, beta_, s0_, s1_ = bn_epi
+        epi = [nhwc(y_), nhwc(out_) if out_ is not None else torch.empty(0, dtype=BF16, device=dy.device), mean_, rstd_,
+               gamma_, beta_, s0_, s1_]
+    _ext().conv_dgrad(dyh, wk, dx, pad, None if add is None else nhwc(add), epi)
     return from_nhwc(dx)
 
 
@@ -236,6 +246,18 @@ def bn_apply(y, s, ss, gamma, beta, eps, residual=None, relu=True, running_mean=
     return from_nhwc(out), mean, rstd
 
 
+def bn_bwd_apply(dz, y, mean, rstd, gamma, s0, s1, dgamma=None, dbeta=None, consumed=None):
+    """Single-pass BN backward for a pre-masked gradient ``dz`` whose per-channel sums were reduced by the producing
+    dgrad's epilogue (``conv_dgrad(..., bn_epi=...)``).  Returns (dy, dgamma, dbeta)."""
+    yh = nhwc(y)
+    c = y.shape[1]
+    dy = torch.empty_like(yh)
+    dgamma = dgamma if dgamma is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    dbeta = dbeta if dbeta is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_bwd_apply(nhwc(dz), yh, mean, rstd, gamma, s0, s1, dgamma, dbeta, dy, consumed)
+    return from_nhwc(dy), dgamma, dbeta
+
+
 def bn_relu_pool(y, s, ss, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1, training=True,
                  consumed=None):
     """BN + ReLU + 3x3/stride-2/pad-1 max-pool in one pass over the raw conv output ``y`` (the stem tail):
@@ -268,6 +290,8 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
 
 import os as _os
 
+DZ_EPILOGUE = _os.environ.get("FLUXDIST_DZ_EPILOGUE", "1") != "0"  # BN-backward reduction in the dgrad epilogue
+DZ_MAX_ROWS = int(_os.environ.get("FLUXDIST_DZ_MAX_ROWS", str(2 * 148 * 128)))
 EPI_STATS = _os.environ.get("FLUXDIST_EPI_STATS", "1") != "0"  # BN statistics in the conv epilogues
 SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
@@ -406,7 +430,12 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
 class _ConvBNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                w_gradbuf, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False):
+                w_gradbuf, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False, own_link=None,
+                src_link=None):
+        # own_link / src_link: a dict shared by this layer (own_link) and the single conv that consumes its output
+        # (src_link there).  The consumer's stride-1 dgrad applies this layer's ReLU mask and reduces the BN-backward
+        # sums in its epilogue (conv_dgrad(bn_epi=...)); this layer's backward is then one elementwise pass.
+        ctx.own_link, ctx.src_link = own_link, src_link
         # pool: fuse a 3x3/2/pad-1 max-pool behind BN+ReLU (ResNet stem): see bn_relu_pool
         # park_link: given to a 1x1/stride-2 projection shortcut whose input is also read by a stride-2 3x3 conv that
         # got the same dict as add_link.  The projection parks its data gradient as a COMPACT [N,H/2,W/2,C] tensor (a
@@ -473,6 +502,8 @@ class _ConvBNAct(torch.autograd.Function):
                 s = ss = gamma  # unused
             out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
         ctx.bn_ws = bn_ws if fused_bn else None
+        if own_link is not None and fused_bn and DZ_EPILOGUE and relu and residual is None and not pool:
+            own_link["bn"] = (y, None, mean, rstd, gamma, beta, bn_ws)
         # residual layers need the saved activation for the ReLU mask; plain layers recompute it from y
         ctx.save_for_backward(x, wl, y, out if (relu and residual is not None) else None, mean, rstd, gamma, beta)
         stem = (not tc) and _is_stem(w.shape, stride, pad, None)
@@ -490,7 +521,15 @@ class _ConvBNAct(torch.autograd.Function):
             dfull = torch.empty(n_, h_, w_, c_, dtype=BF16, device=y.device)
             _ext().maxpool_bwd_idx(ctx.pool_idx, nhwc(dout), dfull, 3, 2, 1)
             dout = from_nhwc(dfull)
-        if ctx.bn_ws is not None:
+        if ctx.own_link is not None and ctx.own_link.pop("dz", False):
+            # dout is already the masked gradient dz; its sums sit in the workspace (reduced by the consumer's dgrad)
+            c_ = y.shape[1]
+            wf = ctx.bn_ws.view(torch.float32)
+            dy, dgamma, dbeta = bn_bwd_apply(dout, y, mean, rstd, gamma, wf[4 + 6 * c_: 4 + 7 * c_],
+                                             wf[4 + 7 * c_: 4 + 8 * c_], ctx.g_gradbuf, ctx.b_gradbuf,
+                                             consumed=ctx.bn_ws[3:4])
+            dres = None
+        elif ctx.bn_ws is not None:
             dy, dgamma, dbeta, dres = bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ctx.bn_ws, relu,
                                                    want_dres=has_res, dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)
         else:
@@ -517,7 +556,19 @@ class _ConvBNAct(torch.autograd.Function):
                     gemm_nn(dyh.reshape(-1, dyh.shape[3]), krsc(wl).reshape(w_shape[0], w_shape[1]))
                     .view(dyh.shape[0], dyh.shape[1], dyh.shape[2], w_shape[1]))
             elif tc:
-                dx = conv_dgrad(dy, wl, x_shape, stride, pad, add=add, add_compact=addc)
+                epi = None
+                src = ctx.src_link
+                # measured (scripts/dz_bench.py, B200, batch 96): the epilogue work is hidden behind the MMAs when a CTA owns
+                # <= 2 output tiles (14x14: dgrad +6 us, BN backward -13 us; 7x7: +5 / -12) but becomes the bottleneck of
+                # the 28x28 layers (4 tiles per CTA: +19 / -15), so those keep the two-pass BN backward
+                rows = x_shape[0] * x_shape[2] * x_shape[3]
+                if src is not None and "bn" in src and stride == 1 and addc is None and rows <= DZ_MAX_ROWS:
+                    y_s, out_s, mean_s, rstd_s, gamma_s, beta_s, ws_s = src["bn"]
+                    cs = y_s.shape[1]
+                    wfs = ws_s.view(torch.float32)
+                    epi = (y_s, out_s, mean_s, rstd_s, gamma_s, beta_s, wfs[4 + 6 * cs: 4 + 7 * cs], wfs[4 + 7 * cs: 4 + 8 * cs])
+                    src["dz"] = True
+                dx = conv_dgrad(dy, wl, x_shape, stride, pad, add=add, add_compact=addc, bn_epi=epi)
             elif stem:
                 dx = torch.nn.grad.conv2d_input(ctx.orig_shape, wl, dy, stride, pad)
             else:
@@ -542,13 +593,14 @@ class _ConvBNAct(torch.autograd.Function):
         # when the gradient already landed in the arena, autograd must not add it a second time
         dw = None if ctx.w_gradbuf is not None else gw
         return (dx, dw, dgamma, dbeta, None, None, dres if has_res else None, None, None, None, None, None, None,
-                None, None, None, None, None, None, None)
+                None, None, None, None, None, None, None, None, None)
 
 
 def conv_bn_act(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp=None,
-                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False):
+                w_gradbuf=None, bn_ws=None, add_link=None, res_link=None, park_link=None, pool=False, own_link=None,
+                src_link=None):
     return _ConvBNAct.apply(x, w, gamma, beta, rm, rv, residual, relu, stride, pad, eps, momentum, training, w_lowp,
-                            w_gradbuf, bn_ws, add_link, res_link, park_link, pool)
+                            w_gradbuf, bn_ws, add_link, res_link, park_link, pool, own_link, src_link)
 
 
 # --------------------------------------------------------------------------- autograd: max-pool, GAP + FC
