@@ -31,8 +31,8 @@ sys.path.insert(0, ROOT)
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "torch", "ddp", "reference"])
     ap.add_argument("--model", default="resnet34", choices=["resnet18", "resnet34", "resnet50", "tiny"])
     ap.add_argument("--batch", type=int, default=96, help="per-GPU batch (README.md:43)")
@@ -218,7 +218,7 @@ def main():
     for _ in range(W):
         run_step()
     barrier()
-    sampler = ClockSampler(local_rank, 100).start() if rank == 0 else None
+    sampler = ClockSampler(local_rank, 10).start() if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(K):

@@ -81,24 +81,78 @@ class PhaseTimes:
 
 
 class ClockSampler:
-    """Background ``nvidia-smi`` sampler (B200_PROFILING.md clocks line)."""
+    """Background SM-clock / throttle-reason sampler for the timed region of a benchmark (B200_PROFILING.md clocks
+    line).  Samples NVML in-process every ``period_ms`` (a query costs microseconds, so even a 100 ms region gets
+    several samples); falls back to a looping ``nvidia-smi`` subprocess when NVML is not importable."""
 
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int = 0, period_ms: int = 100):
+    def __init__(self, gpu_index: int = 0, period_ms: int = 10):
         self.gpu_index = gpu_index
         self.period_ms = period_ms
         self._proc: Optional[subprocess.Popen] = None
         self._lines: List[str] = []
         self._thread: Optional[threading.Thread] = None
+        self._stop = threading.Event()
+        self._sm: List[float] = []
+        self._smax: List[float] = []
+        self._reasons: set = set()
+        self._nvml = None
+
+    # ---------------------------------------------------------------- NVML path
+    def _nvml_handle(self):
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:  # CUDA_VISIBLE_DEVICES-proof: resolve the CUDA device to its NVML handle by UUID
+            import torch
+
+            uuid = str(torch.cuda.get_device_properties(self.gpu_index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+
+    def _sample_nvml(self):
+        nv, h = self._nvml
+        self._sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+        self._smax.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+        for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+            if mask & int(bit):
+                self._reasons.add(name)
 
     def start(self):
         try:
+            self._nvml = self._nvml_handle()
+            self._sample_nvml()
+            self._sm.clear(); self._smax.clear(); self._reasons.clear()  # the probe above may predate the load
+        except Exception:
+            self._nvml = None
+        if self._nvml is not None:
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self._sample_nvml()
+                    except Exception:
+                        pass
+                    self._stop.wait(self.period_ms / 1000.0)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
+            return self
+        try:
             self._proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-i", str(self.gpu_index), "-lms", str(self.period_ms)],
+                 "-i", str(self.gpu_index), "-lms", str(max(self.period_ms, 50))],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self._proc = None
@@ -114,13 +168,21 @@ class ClockSampler:
         return self
 
     def stop(self) -> Dict:
+        self._stop.set()
+        if self._nvml is not None:
+            if self._thread is not None:
+                self._thread.join(timeout=1.0)
+            try:
+                self._sample_nvml()  # one last sample: a very short region still reports what the clock was
+            except Exception:
+                pass
         if self._proc is not None:
             self._proc.terminate()  # exact PID we started
             try:
                 self._proc.wait(timeout=2)
             except Exception:
                 self._proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, reasons = list(self._sm), list(self._smax), set(self._reasons)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self._lines:
             parts = [p.strip() for p in ln.split(",")]
@@ -136,6 +198,5 @@ class ClockSampler:
                     reasons.add(nm)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        # "under load": keep the upper half of samples by clock to drop idle ramp-up
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons),
                 "samples": len(sm)}
