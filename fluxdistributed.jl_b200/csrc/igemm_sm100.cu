@@ -105,22 +105,6 @@ FD_DEVINL void warp_column_sums_smem(const float (&f)[32], float* buf, int lane,
   sumsq += (b[0] + b[1]) + (b[2] + b[3]);
 }
 
-// 32x32 transpose-reduce across a warp: lane l holds v[0..31] (row l of a 32-row block); on return v[0] of lane l is the
-// sum over all 32 lanes of their v[l] (column l).  31 shuffles instead of 32 x 5.
-FD_DEVINL float warp_column_sums(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = up ? v[i] : v[i + off];
-      const float keep = up ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
 template <int BN, int MODE>
 struct Cfg {
   static constexpr int kStages = (BN == 128) ? 6 : 8;
