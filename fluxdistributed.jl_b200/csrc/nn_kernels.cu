@@ -25,6 +25,24 @@ FD_DEVINL V8 pack8(const float* f) {
   for (int i = 0; i < 4; ++i) v.u[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
   return v;
 }
+// Flat-index split for kernels whose per-thread work is small (pooling): four 64-bit div/mod pairs by runtime values
+// were ~250 of the ~390 instructions per thread of maxpool_bwd_idx (ncu: 118 M warp instructions for 9.6 M vectors).
+// All tensors on the ResNet path have < 2^32 vectors, so the split runs in 32-bit unsigned arithmetic.
+FD_DEVINL void split4(long i, int d0, int d1, int d2, int& r0, int& r1, int& r2, int& r3) {
+  if ((unsigned long long)i < 0x100000000ull) {
+    uint32_t t = (uint32_t)i;
+    r0 = (int)(t % (uint32_t)d0); t /= (uint32_t)d0;
+    r1 = (int)(t % (uint32_t)d1); t /= (uint32_t)d1;
+    r2 = (int)(t % (uint32_t)d2);
+    r3 = (int)(t / (uint32_t)d2);
+  } else {
+    long t = i;
+    r0 = (int)(t % d0); t /= d0;
+    r1 = (int)(t % d1); t /= d1;
+    r2 = (int)(t % d2);
+    r3 = (int)(t / d2);
+  }
+}
 FD_DEVINL V8 ldg8(const bf16* p) { return *reinterpret_cast<const V8*>(p); }
 FD_DEVINL void stg8(bf16* p, const V8& v) { *reinterpret_cast<V8*>(p) = v; }
 
@@ -706,12 +724,8 @@ bn_relu_pool3s2_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, uint8
   const int C8 = C / 8;
   const long total = (long)N * P * Q * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    long t = i / C8;
-    const int q = (int)(t % Q);
-    t /= Q;
-    const int p = (int)(t % P);
-    const int n = (int)(t / P);
+    int cv, q, p, n;
+    split4(i, C8, Q, P, cv, q, p, n);
     // sign-flip mask: channels with a negative scale are pooled by their minimum
     uint32_t sm[4];
 #pragma unroll
@@ -779,12 +793,8 @@ maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, uint8_t* 
   const int C8 = C / 8;
   const long total = (long)N * P * Q * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    long t = i / C8;
-    const int q = (int)(t % Q);
-    t /= Q;
-    const int p = (int)(t % P);
-    const int n = (int)(t / P);
+    int cv, q, p, n;
+    split4(i, C8, Q, P, cv, q, p, n);
     float m[8];
     uint32_t am[8];
 #pragma unroll
@@ -826,12 +836,8 @@ maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf
   const int C8 = C / 8;
   const long total = (long)N * P * Q * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    long t = i / C8;
-    const int q = (int)(t % Q);
-    t /= Q;
-    const int p = (int)(t % P);
-    const int n = (int)(t / P);
+    int cv, q, p, n;
+    split4(i, C8, Q, P, cv, q, p, n);
     float m[8];
     int am[8];
 #pragma unroll
@@ -874,18 +880,17 @@ maxpool_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dout, bf
 
 // atomic-free max-pool backward: one thread per (input pixel, 8 channels) gathers from the <= ceil(k/stride)^2 windows
 // that contain it, using the arg-max bytes written by the forward kernel.
+// KT/ST/PT > 0: window geometry known at compile time (3/2/1 for ResNet) so the window-range divisions fold to shifts
+template <int KT, int ST, int PT>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_idx_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N, int H,
-                       int W, int C, int P, int Q, int k, int stride, int pad) {
+                       int W, int C, int P, int Q, int k_rt, int stride_rt, int pad_rt) {
+  const int k = KT ? KT : k_rt, stride = KT ? ST : stride_rt, pad = KT ? PT : pad_rt;
   const int C8 = C / 8;
   const long total = (long)N * H * W * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    long t = i / C8;
-    const int w = (int)(t % W);
-    t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
+    int cv, w, h, n;
+    split4(i, C8, W, H, cv, w, h, n);
     float g[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) g[j] = 0.f;
@@ -957,12 +962,8 @@ upsample_zero_kernel(const bf16* __restrict__ dy, bf16* __restrict__ up, int N, 
   const int C8 = C / 8;
   const long total = (long)N * HU * WU * C8;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i % C8);
-    long t = i / C8;
-    const int w = (int)(t % WU);
-    t /= WU;
-    const int h = (int)(t % HU);
-    const int n = (int)(t / HU);
+    int cv, w, h, n;
+    split4(i, C8, WU, HU, cv, w, h, n);
     V8 v;
     v.u[0] = v.u[1] = v.u[2] = v.u[3] = 0u;
     if (h % stride == 0 && w % stride == 0 && h / stride < P && w / stride < Q)
@@ -1326,8 +1327,14 @@ int fd_maxpool_bwd_idx(const void* idx, const void* dout, void* dx, int N, int H
                        cudaStream_t s) {
   const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
   int grid = grid_for((long)N * H * W * (C / 8), 256, 148 * 16);
-  maxpool_bwd_idx_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(dout),
-                                              reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q, k, stride, pad);
+  if (k == 3 && stride == 2 && pad == 1)
+    maxpool_bwd_idx_kernel<3, 2, 1><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx),
+                                                         reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N,
+                                                         H, W, C, P, Q, k, stride, pad);
+  else
+    maxpool_bwd_idx_kernel<0, 0, 0><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx),
+                                                         reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N,
+                                                         H, W, C, P, Q, k, stride, pad);
   FD_LAUNCH_OK();
   return 0;
 }
