@@ -164,11 +164,12 @@ class NativeComm:
             if a.w16 is not None:
                 h16 = symm.rendezvous(a.w16, gname)
                 w16_ptrs = list(h16.buffer_ptrs)
-            # measured (bench_allreduce.py): on 8 GPUs the in-switch reduction wins at every size (141 vs 215 us at
+            # measured: on 8 GPUs the in-switch reduction wins at every size (bench_allreduce.py: 141 vs 215 us at
             # 64 MB); on 2 GPUs a direct peer read of half the bucket beats the round trip through the switch from
-            # 4 MB up (109 vs 157 us at 64 MB).  FLUXDIST_NVLS=0/1 forces it.
+            # 4 MB up (109 vs 157 us at 64 MB), and on 4 GPUs the ResNet-34 step is 5.46 ms with peer loads vs 5.78 ms
+            # with NVLS (profiles/bench_native_x4_nvls{0,1}.json).  FLUXDIST_NVLS=0/1 forces it.
             env = os.environ.get("FLUXDIST_NVLS", "auto")
-            want_nvls = (env != "0") if env in ("0", "1") else (world > 2 or a.padded * 4 < (4 << 20))
+            want_nvls = (env != "0") if env in ("0", "1") else (world >= 8 or a.padded * 4 < (4 << 20))
             use_nvls = want_nvls and bool(getattr(hg, "multicast_ptr", 0))
             if use_nvls:
                 mc = (int(hg.multicast_ptr), int(hw.multicast_ptr), int(h16.multicast_ptr) if h16 is not None else 0)
