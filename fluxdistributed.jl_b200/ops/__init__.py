@@ -53,9 +53,9 @@ def require_native() -> None:
     extension()
 
 
-from .reference import (bn_apply_ref, bn_bwd_ref, bn_stats_ref, conv_bn_act_ref, conv_dgrad_ref,  # noqa: E402
-                        conv_fprop_ref, conv_wgrad_ref, softmax_ce_ref)
-from .native import (bn_apply, bn_bwd, bn_stats, conv3x3_dgrad, conv3x3_fprop, conv3x3_wgrad, conv_bn_act,  # noqa: E402
-                     conv_dgrad, conv_fprop, conv_wgrad,
-                     fused_update_local, gap_linear, gemm_nn, gemm_nt, gemm_tn, maxpool2d, normalize_u8, softmax_ce, stem_fprop, stem_s2d,
-                     stem_wgrad)
+from .reference import (bn_apply_ref, bn_bwd_apply_ref, bn_bwd_ref, bn_relu_pool_ref, bn_stats_ref,  # noqa: E402
+                        conv_bn_act_ref, conv_dgrad_ref, conv_fprop_ref, conv_wgrad_ref, softmax_ce_ref)
+from .native import (bn_apply, bn_bwd, bn_bwd_apply, bn_bwd_fused, bn_fwd_fused, bn_relu_pool, bn_stats,  # noqa: E402
+                     bn_workspace, conv3x3_dgrad, conv3x3_fprop, conv3x3_wgrad, conv_bn_act, conv_dgrad, conv_fprop,
+                     conv_wgrad, fused_update_local, gap_linear, gemm_nn, gemm_nt, gemm_tn, maxpool2d, normalize_u8,
+                     softmax_ce, stem_fprop, stem_s2d, stem_wgrad)

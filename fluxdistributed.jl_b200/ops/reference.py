@@ -63,3 +63,27 @@ def softmax_ce_ref(logits, labels):
     d = torch.softmax(lf, dim=-1)
     d[torch.arange(lf.shape[0], device=lf.device), labels.long()] -= 1
     return loss, d / lf.shape[0]
+
+
+def bn_relu_pool_ref(y, gamma, beta, eps=1e-5):
+    """Training-mode BN + ReLU + 3x3/stride-2/pad-1 max-pool (oracle of ``ops.bn_relu_pool``)."""
+    import torch.nn.functional as F
+
+    yf = y.float()
+    mean = yf.mean(dim=(0, 2, 3))
+    var = yf.var(dim=(0, 2, 3), unbiased=False)
+    act = torch.relu((yf - mean[None, :, None, None]) * (torch.rsqrt(var + eps) * gamma)[None, :, None, None]
+                     + beta[None, :, None, None])
+    return F.max_pool2d(act, 3, 2, 1)
+
+
+def bn_bwd_apply_ref(dz, y, mean, rstd, gamma):
+    """BN backward for an already ReLU-masked output gradient ``dz`` (oracle of ``ops.bn_bwd_apply``):
+    returns (dy, dgamma, dbeta)."""
+    dzf, yf = dz.float(), y.float()
+    m = yf.numel() // yf.shape[1]
+    xhat = (yf - mean[None, :, None, None]) * rstd[None, :, None, None]
+    dgamma = (dzf * xhat).sum(dim=(0, 2, 3))
+    dbeta = dzf.sum(dim=(0, 2, 3))
+    dy = (gamma * rstd)[None, :, None, None] * (dzf - dbeta[None, :, None, None] / m - xhat * dgamma[None, :, None, None] / m)
+    return dy, dgamma, dbeta
