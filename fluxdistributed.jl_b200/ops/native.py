@@ -4,6 +4,15 @@ Conventions: activations are logically NCHW with ``torch.channels_last`` strides
 (physically NHWC), conv weights logically ``[K,C,R,S]`` channels_last (physically
 KRSC), everything bf16 with fp32 statistics/gradients.  Each function has a plain
 PyTorch oracle in ``ops/reference.py``; ``tests/test_native_gpu.py`` compares them.
+
+Reference call sites these replace: the model forward/backward inside ``gradient(m -> loss(m(x), y), m)``
+(``src/ddp_tasks.jl:80-84``, ``src/sync.jl:140-142``), which the reference leaves to Flux/NNlibCUDA/cuDNN —
+K1-K3 convolutions (``conv_fprop`` / ``conv_dgrad`` / ``conv_wgrad``, halo and stem variants), K4-K6 BatchNorm and
+activation (``bn_apply``, ``bn_bwd_fused``, ``bn_bwd_apply``, statistics in the conv epilogues), K7 pooling
+(``maxpool2d``, ``bn_relu_pool``, GAP inside ``gap_linear``), K8 the Dense head (``gap_linear``), K9 the loss
+(``softmax_ce``; reference ``loss`` at ``src/ddp_tasks.jl:28``), K15/K20 the input path (``normalize_u8``; reference
+``Flux.normalise`` per image at ``src/imagenet.jl:31-34``).  The autograd glue (``_ConvBNAct`` and friends) plays the
+role of Zygote's pullbacks for those layers.
 """
 from __future__ import annotations
 

@@ -1,4 +1,9 @@
-"""Plain PyTorch fp32 reference of every hand-written op (test oracle)."""
+"""Plain PyTorch fp32 reference of every hand-written op (test oracle).
+
+These play the role the library kernels play in the reference (Flux layers lowered to NNlibCUDA/cuDNN inside
+``gradient(...)``, ``src/ddp_tasks.jl:80-84``): the GPU tests compare each sm_100a kernel against them
+(``tests/test_native_gpu.py``), mirroring how the reference tests compare replicas against a single-device run
+(``test/single_device.jl``)."""
 from __future__ import annotations
 
 from typing import Optional, Tuple
