@@ -116,3 +116,37 @@ def test_ensure_synced_checksum():
     assert grp.ensure_synced()
     grp.replicas[1].arena.w32[3] += 1.0
     assert not grp.ensure_synced()
+
+
+@pytest.mark.parametrize("opt", [fd.Momentum(0.05, 0.9), fd.ADAM(1e-2)])
+def test_fused_group_resume_from_state_trees(opt):
+    """Checkpoint/resume of the fused engine: weights + logical optimiser state taken from a group after 2
+    steps and loaded into a fresh group continue exactly like the uninterrupted run."""
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    n = 2
+    devs = fd.fake_devices(n)
+    x, y = _batches(n)
+
+    def run(grp, steps):
+        with ThreadPoolExecutor(n) as ex:
+            for _ in range(steps):
+                futs = [ex.submit(grp.replicas[i].step, x[3 * i:3 * i + 3], y[3 * i:3 * i + 3], fd.logitcrossentropy)
+                        for i in range(n)]
+                [f.result() for f in futs]
+
+    full = FusedGroup.for_threads([copy.deepcopy(base) for _ in range(n)], devs, opt, dtype=torch.float32)
+    run(full, 4)
+    first = FusedGroup.for_threads([copy.deepcopy(base) for _ in range(n)], devs, opt, dtype=torch.float32)
+    run(first, 2)
+    first.sync_to_modules()
+    sts = first.state_trees()
+    steps_done = first.replicas[0].step_count
+    resumed_models = [copy.deepcopy(r.model) for r in first.replicas]
+    second = FusedGroup.for_threads(resumed_models, devs, opt, dtype=torch.float32)
+    for r, d in zip(second.replicas, devs):
+        r.load_state_tree(sts[d], step_count=steps_done)
+    run(second, 2)
+    for a, b in zip(second.replicas[0].model.parameters(), full.replicas[0].model.parameters()):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert compare(second.state_trees()[devs[0]], full.state_trees()[devs[0]], 1e-5, 1e-6)

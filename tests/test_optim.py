@@ -87,3 +87,62 @@ def test_flat_step_equals_tree_update():
             flat_step(opt, w, gf, slots, step)
             ref = torch.cat([p.detach().reshape(-1) for p in m.parameters()])
             assert torch.allclose(w, ref, atol=1e-6), type(opt).__name__
+
+
+def _run_rule(opt, steps=4):
+    torch.manual_seed(0)
+    x = torch.randn(7, 5)
+    gs = [torch.randn(7, 5) for _ in range(steps)]
+    st = opt.init(x)
+    for g in gs:
+        st, x = opt.apply(st, x, g)
+    return x, gs
+
+
+def test_descent_matches_torch_sgd():
+    x, gs = _run_rule(fd.Descent(0.05))
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(7, 5))
+    o = torch.optim.SGD([p], lr=0.05)
+    for g in gs:
+        p.grad = g.clone()
+        o.step()
+    assert torch.allclose(x, p.detach(), atol=1e-6)
+
+
+def test_momentum_matches_torch_sgd_momentum_reparametrised():
+    """Optimisers' Momentum (v <- rho v - eta g; x <- x + v) equals torch's (b <- rho b + g; x <- x - lr b) with
+    lr = eta (constant learning rate): v = -eta * b."""
+    x, gs = _run_rule(fd.Momentum(0.01, 0.9))
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(7, 5))
+    o = torch.optim.SGD([p], lr=0.01, momentum=0.9)
+    for g in gs:
+        p.grad = g.clone()
+        o.step()
+    assert torch.allclose(x, p.detach(), atol=1e-6)
+
+
+def test_nesterov_matches_torch_sgd_nesterov():
+    x, gs = _run_rule(fd.Nesterov(0.01, 0.9))
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(7, 5))
+    o = torch.optim.SGD([p], lr=0.01, momentum=0.9, nesterov=True)
+    for g in gs:
+        p.grad = g.clone()
+        o.step()
+    assert torch.allclose(x, p.detach(), atol=1e-6)
+
+
+def test_adamw_decoupled_decay_matches_torch_adamw_modulo_eps():
+    """Same convention difference as ADAM (eps added to sqrt(v_hat) here and in torch; Optimisers 0.1 semantics) — with
+    eps tiny the trajectories agree; the decay term is eta*decay*x on the PRE-update weights in both."""
+    opt = fd.AdamW(eta=1e-2, beta=(0.9, 0.99), eps=1e-12, decay=0.1)
+    x, gs = _run_rule(opt, steps=5)
+    torch.manual_seed(0)
+    p = torch.nn.Parameter(torch.randn(7, 5))
+    o = torch.optim.AdamW([p], lr=1e-2, betas=(0.9, 0.99), eps=1e-12, weight_decay=0.1)
+    for g in gs:
+        p.grad = g.clone()
+        o.step()
+    assert torch.allclose(x, p.detach(), atol=2e-5)
