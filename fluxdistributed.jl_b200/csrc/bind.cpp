@@ -409,6 +409,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   });
   m.def("num_sms", &fd_num_sms);
   m.def("set_cluster_multicast", &fd_set_cluster_multicast);
+  m.def("set_epilogue8", &fd_set_epilogue8);
   m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
   fd_bind_staging(m);
 }

@@ -3,7 +3,8 @@
 #include <cuda_runtime.h>
 
 int fd_num_sms();
-void fd_set_cluster_multicast(int on);  // 2-CTA cluster + TMA multicast of the filter tile in conv fprop/dgrad (default on)
+void fd_set_cluster_multicast(int on);
+void fd_set_epilogue8(int on);  // eight-epilogue-warp conv kernels (experimental; default off, env FLUXDIST_EPI8=1)  // 2-CTA cluster + TMA multicast of the filter tile in conv fprop/dgrad (default on)
 int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);

@@ -18,6 +18,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -105,9 +106,14 @@ FD_DEVINL void warp_column_sums_smem(const float (&f)[32], float* buf, int lane,
   sumsq += (b[0] + b[1]) + (b[2] + b[3]);
 }
 
-template <int BN, int MODE>
+// E8: eight epilogue warps (two per SM sub-partition, BN/2 columns each) instead of four.  One warp per scheduler issues
+// its dependent epilogue instructions back to back (IPC ~0.2); a second warp on the same scheduler fills those slots.
+// One operand stage is given up for the larger per-warp reduction scratch.
+template <int BN, int MODE, bool E8 = false>
 struct Cfg {
-  static constexpr int kStages = (BN == 128) ? 6 : 8;
+  static constexpr int kStages = ((BN == 128) ? 6 : 8) - (E8 ? 1 : 0);
+  static constexpr int kEpiWarps = E8 ? 8 : 4;
+  static constexpr int kThreadsCfg = 64 + 32 * kEpiWarps;
   static constexpr int A_BYTES = BM * BK * 2;  // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;  // 8/16 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -119,10 +125,10 @@ struct Cfg {
 // they need the same B (filter) tile: each CTA fetches HALF of it and the copy engine multicasts it into both CTAs'
 // shared memory (.multicast::cluster), halving the L2 traffic of the operand that every m-tile re-reads.  Shared-memory
 // slots are released cluster-wide (tcgen05.commit ... .multicast::cluster on both CTAs' empty barriers).
-template <int BN, int MODE, bool MC = false, bool BZ = false>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int MODE, bool MC = false, bool BZ = false, bool E8 = false>
+__global__ void __launch_bounds__(E8 ? 320 : kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const KParams P) {
-  using C = Cfg<BN, MODE>;
+  using C = Cfg<BN, MODE, E8>;
   constexpr int kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -148,7 +154,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * C::kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -328,20 +334,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     float* const red0 = bz ? P.bz_s1 : P.st_sum;  // st_s: sum x (fprop) / sum dz (dgrad)
     float* const red1 = bz ? P.bz_s0 : P.st_sq;   // st_q: sum x^2 (fprop) / sum dz*(y-mean) (dgrad)
     // per epilogue warp: mean | gamma*rstd | shift of the tile's channels (static shared: plain LDS, no generic loads)
-    __shared__ float bnpar_all[bz ? 4 * 3 * BN : 4];
-    __shared__ __align__(16) float colred_all[(MODE == MODE_FPROP || bz) ? 4 * 32 * 36 : 4];
+    __shared__ float bnpar_all[bz ? C::kEpiWarps * 3 * BN : 4];
+    __shared__ __align__(16) float colred_all[(MODE == MODE_FPROP || bz) ? C::kEpiWarps * 32 * 36 : 4];
+    // columns this warp drains: all of them (4 epilogue warps) or one half (8: warps 2-5 the lower, 6-9 the upper half)
+    const int c_begin = E8 ? ((warp - 2) >> 2) * (BN / 2) : 0;
+    constexpr int c_count = E8 ? BN / 2 : BN;
     float* const colred = colred_all + ((MODE == MODE_FPROP || bz) ? (warp - 2) * 32 * 36 : 0);
     float* const bnpar = bnpar_all + (bz ? (warp - 2) * 3 * BN : 0);
-    float st_s[BN / 32], st_q[BN / 32];  // this lane's channel (c0 + lane) of each 32-column chunk, over this CTA's tiles
+    float st_s[c_count / 32], st_q[c_count / 32];  // this lane's channel (c0 + lane) of each 32-column chunk, over this CTA's tiles
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) st_s[i] = st_q[i] = 0.f;
+    for (int i = 0; i < c_count / 32; ++i) st_s[i] = st_q[i] = 0.f;
     int st_nt = -1;
     auto flush_stats = [&]() {
       if (st_nt >= 0) {
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {
-          atomicAdd(red0 + st_nt * BN + i * 32 + lane, st_s[i]);
-          atomicAdd(red1 + st_nt * BN + i * 32 + lane, st_q[i]);
+        for (int i = 0; i < c_count / 32; ++i) {
+          atomicAdd(red0 + st_nt * BN + c_begin + i * 32 + lane, st_s[i]);
+          atomicAdd(red1 + st_nt * BN + c_begin + i * 32 + lane, st_q[i]);
           st_s[i] = st_q[i] = 0.f;
         }
       }
@@ -369,11 +378,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
       const int row = m0 + quad * 32 + lane;
       // dz epilogue: the BN layer's y tile is requested BEFORE waiting for the accumulator, so its global-memory
       // latency overlaps the MMAs of this tile instead of serialising with the TMEM reads
-      uint4 ypre[bz ? BN / 8 : 1];
+      uint4 ypre[bz ? c_count / 8 : 1];
       if (bz) {
-        const bf16* yrow = reinterpret_cast<const bf16*>(P.bz_y) + (long)row * P.ldo + nt * BN;
+        const bf16* yrow = reinterpret_cast<const bf16*>(P.bz_y) + (long)row * P.ldo + nt * BN + c_begin;
 #pragma unroll
-        for (int j = 0; j < BN / 8; ++j) ypre[j] = (row < P.M) ? *reinterpret_cast<const uint4*>(yrow + j * 8) : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < c_count / 8; ++j) ypre[j] = (row < P.M) ? *reinterpret_cast<const uint4*>(yrow + j * 8) : make_uint4(0, 0, 0, 0);
       }
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
@@ -384,7 +393,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
         has_k = b1 > b0;
       }
 #pragma unroll
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc0 = 0; cc0 < c_count; cc0 += 32) {
+        const int c0 = c_begin + cc0;
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c0, v);
         tmem_ld_wait();
@@ -395,7 +405,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const long off = (long)row * P.ldo + nt * BN + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
-            uint4 yv = ypre[(c0 + j) / 8], av = make_uint4(0, 0, 0, 0), ov = av;
+            uint4 yv = ypre[(cc0 + j) / 8], av = make_uint4(0, 0, 0, 0), ov = av;
             if (live) {
               if (P.add) av = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.add) + off + j);
               if (P.bz_out) ov = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_out) + off + j);
@@ -418,14 +428,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
             }
           }
           float unused = 0.f;
-          warp_column_sums_smem(f, colred, lane, st_s[c0 / 32], unused);
-          warp_column_sums_smem(q, colred, lane, st_q[c0 / 32], unused);
+          warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], unused);
+          warp_column_sums_smem(q, colred, lane, st_q[cc0 / 32], unused);
           added = true;  // `add` is already inside v
         } else if (do_stats) {  // rows past M are TMA zero-fill: they add nothing
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          warp_column_sums_smem(f, colred, lane, st_s[c0 / 32], st_q[c0 / 32]);
+          warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], st_q[cc0 / 32]);
         }
         if (row < P.M && has_k) {
           if (MODE == MODE_WGRAD) {
@@ -585,20 +595,20 @@ int make_map_im2col(CUtensorMap* m, const void* base, int N, int H, int W, int C
   return 0;
 }
 
-template <int BN, int MODE, bool BZ = false>
+template <int BN, int MODE, bool BZ = false, bool E8 = false>
 int launch(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStream_t s) {
-  using C = Cfg<BN, MODE>;
+  using C = Cfg<BN, MODE, E8>;
   static bool attr_set[16] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 15]) {
-    FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE, false, BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    FD_CUDA_CHECK(cudaFuncSetAttribute(igemm_kernel<BN, MODE, false, BZ, E8>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set[dev & 15] = true;
   }
   int tiles = p.m_tiles * p.n_tiles * p.splits;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
   if (grid < 1) grid = 1;
-  igemm_kernel<BN, MODE, false, BZ><<<grid, kThreads, C::SMEM_BYTES, s>>>(a, b, p);
+  igemm_kernel<BN, MODE, false, BZ, E8><<<grid, C::kThreadsCfg, C::SMEM_BYTES, s>>>(a, b, p);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -695,6 +705,17 @@ int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int o
 
 static int g_use_mc = 1;
 void fd_set_cluster_multicast(int on) { g_use_mc = on; }
+// eight-epilogue-warp instantiations (Cfg::E8) of the conv kernels: compiled, not yet dispatched by default (validated
+// first thing next round); FLUXDIST_EPI8=1 or fd_set_epilogue8(1) selects them
+static int g_epi8 = -1;
+void fd_set_epilogue8(int on) { g_epi8 = on; }
+static bool use_epi8() {
+  if (g_epi8 < 0) {
+    const char* e = getenv("FLUXDIST_EPI8");
+    g_epi8 = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_epi8 == 1;
+}
 
 int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K, int R,
                   int S, int stride, int pad, cudaStream_t s) {
@@ -724,6 +745,7 @@ int fd_conv_fprop(const void* x, const void* w, void* y, float* sum, float* sums
   p.out = y; p.ldo = K; p.out_fp32 = 0;
   p.st_sum = sum; p.st_sq = sumsq;  // accumulated into: the caller provides zeroed buffers
   if (mc) return launch_mc<128, MODE_FPROP>(ma, mb, p, s);
+  if (use_epi8()) return bn == 64 ? launch<64, MODE_FPROP, false, true>(ma, mb, p, s) : launch<128, MODE_FPROP, false, true>(ma, mb, p, s);
   return bn == 64 ? launch<64, MODE_FPROP>(ma, mb, p, s) : launch<128, MODE_FPROP>(ma, mb, p, s);
 }
 
@@ -756,8 +778,10 @@ int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, cons
   if (bz) {
     p.bz_y = bz->y; p.bz_out = bz->out; p.bz_mean = bz->mean; p.bz_rstd = bz->rstd; p.bz_gamma = bz->gamma;
     p.bz_beta = bz->beta; p.bz_s0 = bz->s0; p.bz_s1 = bz->s1;
+    if (use_epi8()) return bn == 64 ? launch<64, MODE_DGRAD, true, true>(ma, mb, p, s) : launch<128, MODE_DGRAD, true, true>(ma, mb, p, s);
     return bn == 64 ? launch<64, MODE_DGRAD, true>(ma, mb, p, s) : launch<128, MODE_DGRAD, true>(ma, mb, p, s);
   }
+  if (use_epi8()) return bn == 64 ? launch<64, MODE_DGRAD, false, true>(ma, mb, p, s) : launch<128, MODE_DGRAD, false, true>(ma, mb, p, s);
   return bn == 64 ? launch<64, MODE_DGRAD>(ma, mb, p, s) : launch<128, MODE_DGRAD>(ma, mb, p, s);
 }
 
@@ -824,6 +848,7 @@ int fd_conv_dgrad_s2(const void* dy, const void* w, void* dx, const void* add_co
   p.S = S; p.R = R; p.C_chunks = K / 64; p.Ctot = C;
   p.sub_H = H; p.sub_W = W;
   p.out = dx; p.ldo = C; p.out_fp32 = 0; p.add = (p.sub_add_cls >= 0) ? add_compact : nullptr;
+  if (use_epi8()) return bn == 64 ? launch<64, MODE_DGRAD_S2, false, true>(ma, mb, p, s) : launch<128, MODE_DGRAD_S2, false, true>(ma, mb, p, s);
   return bn == 64 ? launch<64, MODE_DGRAD_S2>(ma, mb, p, s) : launch<128, MODE_DGRAD_S2>(ma, mb, p, s);
 }
 
