@@ -32,6 +32,16 @@ class BasicBlock(nn.Module):
             link, mid = {}, {}
             # `mid`: conv1's output is consumed by conv2 only, so conv2's dgrad epilogue may do the reduction pass of
             # conv1's BN backward (mask + per-channel sums) and hand over the masked gradient
+            from ..ops import native as _nv
+
+            if _nv.DZ_CHAIN and getattr(self, "_chain_ok", False):
+                # experimental: the previous block's output is consumed by this block only (guaranteed by ResNet, which
+                # sets _chain_ok), so conv1's dgrad may also finish the previous block's last BN layer ("tail" link)
+                tail = {"tail": True}
+                out = self.conv2(self.conv1(x, add_link=link, own_link=mid, src_link=getattr(x, "_fd_tail", None)),
+                                 residual=x, res_link=link, src_link=mid, own_link=tail)
+                out._fd_tail = tail
+                return out
             return self.conv2(self.conv1(x, add_link=link, own_link=mid), residual=x, res_link=link, src_link=mid)
         if self.downsample is not None and self.conv1.stride == 2 and self.downsample.stride == 2 and x.is_cuda \
                 and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and self.conv1.cin % 64 == 0 \
@@ -77,6 +87,9 @@ class ResNet(nn.Module):
                 cin = planes * block.expansion
             stages.append(nn.Sequential(*blocks))
         self.layer1, self.layer2, self.layer3, self.layer4 = stages
+        for stage in stages:  # inside a stage every block output feeds the next block only (see BasicBlock.forward)
+            for blk in stage:
+                blk._chain_ok = True
         self.head = Head(cin, nclasses)
         self.nclasses = nclasses
 

@@ -301,6 +301,9 @@ import os as _os
 
 DZ_EPILOGUE = _os.environ.get("FLUXDIST_DZ_EPILOGUE", "1") != "0"  # BN-backward reduction in the dgrad epilogue
 DZ_MAX_ROWS = int(_os.environ.get("FLUXDIST_DZ_MAX_ROWS", str(2 * 148 * 128)))
+# experimental (not validated on a GPU yet, default off): chain the dz epilogue across blocks — the next block's first conv
+# masks and reduces for this block's LAST BN layer (mask from the post-residual activation)
+DZ_CHAIN = _os.environ.get("FLUXDIST_DZ_CHAIN", "0") == "1"
 EPI_STATS = _os.environ.get("FLUXDIST_EPI_STATS", "1") != "0"  # BN statistics in the conv epilogues
 SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
@@ -511,8 +514,10 @@ class _ConvBNAct(torch.autograd.Function):
                 s = ss = gamma  # unused
             out, mean, rstd = bn_apply(y, s, ss, gamma, beta, eps, residual, relu, rm, rv, momentum, training)
         ctx.bn_ws = bn_ws if fused_bn else None
-        if own_link is not None and fused_bn and DZ_EPILOGUE and relu and residual is None and not pool:
-            own_link["bn"] = (y, None, mean, rstd, gamma, beta, bn_ws)
+        if own_link is not None and fused_bn and DZ_EPILOGUE and relu and not pool \
+                and (residual is None or own_link.get("tail")):
+            # residual layers ("tail" links, experimental): the ReLU mask comes from the post-residual activation
+            own_link["bn"] = (y, out if residual is not None else None, mean, rstd, gamma, beta, bn_ws)
         # residual layers need the saved activation for the ReLU mask; plain layers recompute it from y
         ctx.save_for_backward(x, wl, y, out if (relu and residual is not None) else None, mean, rstd, gamma, beta)
         stem = (not tc) and _is_stem(w.shape, stride, pad, None)
@@ -537,7 +542,7 @@ class _ConvBNAct(torch.autograd.Function):
             dy, dgamma, dbeta = bn_bwd_apply(dout, y, mean, rstd, gamma, wf[4 + 6 * c_: 4 + 7 * c_],
                                              wf[4 + 7 * c_: 4 + 8 * c_], ctx.g_gradbuf, ctx.b_gradbuf,
                                              consumed=ctx.bn_ws[3:4])
-            dres = None
+            dres = dout if has_res else None  # the masked gradient is also what flows into the skip connection
         elif ctx.bn_ws is not None:
             dy, dgamma, dbeta, dres = bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ctx.bn_ws, relu,
                                                    want_dres=has_res, dgamma=ctx.g_gradbuf, dbeta=ctx.b_gradbuf)

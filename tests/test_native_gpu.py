@@ -2,6 +2,7 @@
 same op.  All tests need a GPU and the in-tree extension — they fail loudly
 (not skip) if the extension cannot be loaded on a CUDA box."""
 import copy
+import os
 
 import pytest
 import torch
@@ -200,6 +201,43 @@ def test_block_dz_epilogue_matches_two_pass_bn_backward():
         NV.DZ_EPILOGUE = True
         set_backend("auto")
     assert n_on == n_off  # same launch count: one BN-backward kernel either way, but the fused one is single-pass
+    for a, b in zip(on, off):
+        assert rel_err(a, b) < 2e-2
+
+
+@pytest.mark.skipif(os.environ.get("FLUXDIST_DZ_CHAIN") != "1", reason="experimental path: run with FLUXDIST_DZ_CHAIN=1")
+def test_stage_dz_chain_matches_unchained():
+    """Two identity blocks of a 14x14x256 stage: with the dz epilogue chained across the block boundary (the second
+    block's first conv finishes the first block's last BN layer) the gradients equal the unchained run."""
+    from fluxdist.models.resnet import BasicBlock
+    from fluxdist.nn import set_backend
+    from fluxdist.ops import native as NV
+
+    torch.manual_seed(0)
+    set_backend("native")
+    try:
+        stage = torch.nn.Sequential(BasicBlock(256, 256), BasicBlock(256, 256)).cuda().to(memory_format=torch.channels_last)
+        for b_ in stage:
+            b_._chain_ok = True
+        x = cl(torch.randn(8, 256, 14, 14, device="cuda").to(BF)).requires_grad_(True)
+        g = cl(torch.randn(8, 256, 14, 14, device="cuda").to(BF))
+
+        def run():
+            for p_ in stage.parameters():
+                p_.grad = None
+            x.grad = None
+            stage(x).backward(g)
+            torch.cuda.synchronize()
+            return [x.grad.float().clone()] + [p_.grad.float().clone() for p_ in stage.parameters()]
+
+        run()
+        NV.DZ_CHAIN = True
+        on = run()
+        NV.DZ_CHAIN = False
+        off = run()
+    finally:
+        NV.DZ_CHAIN = os.environ.get("FLUXDIST_DZ_CHAIN") == "1"
+        set_backend("auto")
     for a, b in zip(on, off):
         assert rel_err(a, b) < 2e-2
 
