@@ -34,9 +34,9 @@ def _cuda_home() -> str:
     raise RuntimeError("nvcc not found")
 
 
-def ext_path() -> str:
+def ext_path(name: str = "_C") -> str:
     suffix = sysconfig.get_config_var("EXT_SUFFIX") or ".so"
-    return os.path.join(HERE, "_C" + suffix)
+    return os.path.join(HERE, name + suffix)
 
 
 def build(verbose: bool = False, force: bool = False) -> str:
@@ -50,7 +50,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
     inc = [f"-I{p}" for p in ce.include_paths()] + [f"-I{sysconfig.get_paths()['include']}", f"-I{CSRC}",
                                                    f"-I{cuda}/include"]
     cxx11 = int(torch._C._GLIBCXX_USE_CXX11_ABI)
-    cxx_flags = ["-O2", "-std=c++17", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={cxx11}", "-DTORCH_EXTENSION_NAME=_C",
+    cxx_flags = ["-O2", "-std=c++17", "-fPIC", f"-D_GLIBCXX_USE_CXX11_ABI={cxx11}",
                  "-DTORCH_API_INCLUDE_EXTENSION_H", "-Wno-deprecated-declarations"]
     torch_lib = os.path.join(os.path.dirname(torch.__file__), "lib")
     out = ext_path()
@@ -67,7 +67,7 @@ def build(verbose: bool = False, force: bool = False) -> str:
         "  depfile = $out.d",
         "  deps = gcc",
         "rule cxx",
-        "  command = $cxx $cxxflags -MMD -MF $out.d -c $in -o $out",
+        "  command = $cxx $cxxflags -DTORCH_EXTENSION_NAME=$modname -MMD -MF $out.d -c $in -o $out",
         "  depfile = $out.d",
         "  deps = gcc",
         "rule link",
@@ -82,8 +82,23 @@ def build(verbose: bool = False, force: bool = False) -> str:
         o = os.path.join(BUILD, os.path.basename(s) + ".o")
         objs.append(o)
         lines.append(f"build {o}: cxx {s}")
+        lines.append("  modname = _C")
     lines.append(f"build {out}: link {' '.join(objs)}")
-    lines.append(f"default {out}")
+    # hardware probes (scripts/probe_*.py): their own module, never linked into the product extension
+    pobjs = []
+    pout = ext_path("_Cprobe")
+    for s in sorted(glob.glob(os.path.join(CSRC, "probes", "*.cu"))):
+        o = os.path.join(BUILD, "probe_" + os.path.basename(s) + ".o")
+        pobjs.append(o)
+        lines.append(f"build {o}: nvcc {s}")
+    for s in sorted(glob.glob(os.path.join(CSRC, "probes", "*.cpp"))):
+        o = os.path.join(BUILD, "probe_" + os.path.basename(s) + ".o")
+        pobjs.append(o)
+        lines.append(f"build {o}: cxx {s}")
+        lines.append("  modname = _Cprobe")
+    if pobjs:
+        lines.append(f"build {pout}: link {' '.join(pobjs)}")
+    lines.append(f"default {out}" + (f" {pout}" if pobjs else ""))
     with open(os.path.join(BUILD, "build.ninja"), "w") as f:
         f.write("\n".join(lines) + "\n")
     if force:

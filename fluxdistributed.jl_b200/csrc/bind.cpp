@@ -14,10 +14,6 @@
 
 const char* fd_last_error();
 long fd_launch_count();
-int fd_probe_shift32(const void* A, const void* B, float* D, int rows, int shift, int sbo, int mn_major, cudaStream_t s);
-int fd_probe_mma_rate(long long* out, int bn, int reps, int shift, int sbo, int grid, int flavor, cudaStream_t s);
-int fd_probe_shift(const void* A, const void* B, float* D, int rows, int shift, int sbo, int base_off, int mn_major,
-                   int nk16, cudaStream_t s);
 
 namespace {
 
@@ -71,6 +67,8 @@ struct FusedPlan {
     for (size_t i = 0; i < 8; ++i) a.h[i] = i < h.size() ? (float)h[i] : 0.f;
     a.grad_scale = (float)grad_scale;
   }
+  void set_hyper_dev(int64_t ptr) { a.hyper_dev = reinterpret_cast<const float*>(ptr); }
+  void set_step_ptr(int64_t ptr) { a.step_dev = reinterpret_cast<int*>(ptr); }
   void set_max_spins(long long s) { a.max_spins = s; }
   void launch() {
     c10::cuda::CUDAGuard guard(device);
@@ -266,6 +264,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                     std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, int64_t, int64_t, int64_t,
                     int64_t, int64_t, int64_t, int64_t, int, int>())
       .def("set_hyper", &FusedPlan::set_hyper)
+      .def("set_hyper_dev", &FusedPlan::set_hyper_dev)
+      .def("set_step_ptr", &FusedPlan::set_step_ptr)
       .def("set_max_spins", &FusedPlan::set_max_spins)
       .def("launch", &FusedPlan::launch)
       .def_readonly("grid", &FusedPlan::grid);
@@ -324,6 +324,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_stem_wgrad(dy.data_ptr(), x2.data_ptr(), dw2.data_ptr<float>(), (int)x2.size(0), (int)x2.size(1), (int)x2.size(2),
                         cur_stream()), "stem_wgrad");
   });
+  m.def("bn_set_reserve", &fd_bn_set_reserve, "CTA slots the single-launch BN kernels leave free for a concurrent bucket kernel");
   m.def("bn_ws_bytes", [](int C) { return (int64_t)fd_bn_ws_bytes(C); });
   m.def("bn_fwd_fused", [](at::Tensor y, c10::optional<at::Tensor> res, at::Tensor out, at::Tensor gamma, at::Tensor beta,
                            c10::optional<at::Tensor> run_mean, c10::optional<at::Tensor> run_var, at::Tensor save_mean,
@@ -393,23 +394,10 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bias_add", &bias_add);
   m.def("colsum", &colsum);
   m.def("enable_peer_access", &enable_peer_access);
-  m.def("probe_shift32", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, bool mn_major) {
-    c10::cuda::CUDAGuard guard(A.device());
-    check(fd_probe_shift32(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, mn_major, cur_stream()),
-          "probe_shift32");
-  });
-  m.def("probe_mma_rate", [](at::Tensor out, int bn, int reps, int shift, int sbo, int grid, int flavor) {
-    c10::cuda::CUDAGuard guard(out.device());
-    check(fd_probe_mma_rate(reinterpret_cast<long long*>(out.data_ptr<int64_t>()), bn, reps, shift, sbo, grid, flavor, cur_stream()), "probe_mma_rate");
-  });
-  m.def("probe_shift", [](at::Tensor A, at::Tensor B, at::Tensor D, int shift, int sbo, int base_off, bool mn_major, int nk16) {
-    c10::cuda::CUDAGuard guard(A.device());
-    check(fd_probe_shift(A.data_ptr(), B.data_ptr(), D.data_ptr<float>(), (int)A.size(0), shift, sbo, base_off, mn_major, nk16,
-                         cur_stream()), "probe_shift");
-  });
   m.def("num_sms", &fd_num_sms);
   m.def("set_cluster_multicast", &fd_set_cluster_multicast);
   m.def("set_epilogue8", &fd_set_epilogue8);
+  m.def("set_tile_shape", &fd_set_tile_shape, "force the conv CTA tile shape (bn, m-tiles per CTA); (0, 0) = automatic");
   m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
   fd_bind_staging(m);
 }

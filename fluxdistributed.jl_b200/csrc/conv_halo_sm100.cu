@@ -417,7 +417,7 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, 
   p.tiles_h = (H + TH - 1) / TH; p.tiles_w = (W + TW - 1) / TW;
   p.m_tiles = N * p.tiles_h * p.tiles_w;
   p.wcols = wcols; p.out = out; p.sum = sum; p.sumsq = sumsq; p.add = add;
-  p.dbg = variant >> 8; variant &= 255;
+  p.dbg = variant >> 9; variant &= 255;  // bit 8 = statistics buffers pre-zeroed (fd_conv3x3_fprop), bits 9+ = ablation
   // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
   const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
   const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048;
@@ -823,7 +823,7 @@ int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int
 int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K,
                      int variant, cudaStream_t s) {
   const bool prezeroed = (variant & 0x100) != 0;  // the statistics buffers are known to be zero (see bn_apply's `consumed`)
-  variant &= 0xff;
+  variant &= ~0x100;
   if (sum && !prezeroed) {
     FD_CUDA_CHECK(cudaMemsetAsync(sum, 0, K * sizeof(float), s));
     FD_CUDA_CHECK(cudaMemsetAsync(sumsq, 0, K * sizeof(float), s));

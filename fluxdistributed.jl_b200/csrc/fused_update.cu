@@ -87,6 +87,11 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_update_kernel(const 
   // step counter (Adam bias correction) lives on the device so a captured graph stays valid
   const int t = *A.step_dev + 1;
   Hyper h{A.h[0], A.h[1], A.h[2], A.h[3], A.h[4]};
+  float grad_scale = A.grad_scale;
+  if (A.hyper_dev != nullptr) {  // hyper-parameters live in device memory: graph replays see set_opt()
+    h.eta = A.hyper_dev[0]; h.a = A.hyper_dev[1]; h.b = A.hyper_dev[2]; h.eps = A.hyper_dev[3]; h.decay = A.hyper_dev[4];
+    grad_scale = A.hyper_dev[7];
+  }
   float c1inv = 1.f, c2inv = 1.f;
   if constexpr (RULE == FD_RULE_ADAM || RULE == FD_RULE_ADAMW) {
     c1inv = 1.f / (1.f - powf(h.a, (float)t));
@@ -133,8 +138,8 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_update_kernel(const 
     for (int u = 0; u < kUnroll; ++u) {
       if (idx[u] >= slice4) continue;
       const long e = (base4 + idx[u]) * 4;
-      float gg[4] = {g[u].x * inv_w * A.grad_scale, g[u].y * inv_w * A.grad_scale, g[u].z * inv_w * A.grad_scale,
-                     g[u].w * inv_w * A.grad_scale};
+      const float gs = inv_w * grad_scale;
+      float gg[4] = {g[u].x * gs, g[u].y * gs, g[u].z * gs, g[u].w * gs};
       float4 w4 = *reinterpret_cast<const float4*>(A.w32 + e);
       float ww[4] = {w4.x, w4.y, w4.z, w4.w};
       float s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0};

@@ -13,7 +13,9 @@ struct FusedArgs {
   long n;                               // elements in this bucket (multiple of 4*world)
   long fp32_bcast_from;                 // elements >= this offset are also broadcast in fp32
   float grad_scale;                     // extra scale on the mean gradient (loss-scale inverse)
-  float h[8];                           // eta, a(rho|beta1), b(beta2), eps, decay
+  float h[8];                           // eta, a(rho|beta1), b(beta2), eps, decay (used when hyper_dev is null)
+  const float* hyper_dev;               // device copy of {h[0..4], -, -, grad_scale}: read at run time, so a captured
+                                        // CUDA graph follows set_opt / LR schedules without re-capture
   const float* g[FD_MAX_WORLD];         // gradient arena of every rank (peer-mapped), bucket base
   float* w32;                           // local fp32 master
   float* s0;                            // local moment 1 (momentum / Adam m)

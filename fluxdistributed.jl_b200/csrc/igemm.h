@@ -4,7 +4,8 @@
 
 int fd_num_sms();
 void fd_set_cluster_multicast(int on);
-void fd_set_epilogue8(int on);  // eight-epilogue-warp conv kernels (experimental; default off, env FLUXDIST_EPI8=1)  // 2-CTA cluster + TMA multicast of the filter tile in conv fprop/dgrad (default on)
+void fd_set_epilogue8(int on);  // eight-epilogue-warp conv kernels (default since round 2; env FLUXDIST_EPI8=0 for four)
+void fd_set_tile_shape(int bn, int mt);  // force the conv CTA tile (bn in {64,128,256}, mt m-tiles per CTA; 0 = automatic)
 int fd_gemm_nt(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_nn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);
 int fd_gemm_tn(const void* A, const void* B, void* D, int M, int N, int K, int out_fp32, cudaStream_t s);

@@ -1428,6 +1428,12 @@ int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s) {
 
 // ---- single-launch BN (grid-barrier kernels).  `ws` is a per-layer workspace: [counter, gen, pad, pad] (uint)
 // followed by two [2][C] float accumulators (double-buffered by launch parity).
+// CTA slots the grid-barrier kernels leave free: a bucket of the fused all-reduce+update kernel may be running on the
+// communication stream at the same time (parallel/native_comm.py), and every CTA of a grid-barrier kernel must be
+// resident for the barrier to complete.
+static int g_bn_reserve = 0;
+void fd_bn_set_reserve(int ctas) { g_bn_reserve = ctas < 0 ? 0 : ctas; }
+
 static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
   static int sms = 0;
   if (!sms) {
@@ -1451,7 +1457,8 @@ static int bn_fused_grid(const void* fn, size_t smem, long M, int C) {
   const long bytes = M * C * 2;
   const long ck = chunk ? chunk : (bytes < (8L << 20) ? 32768 : 65536);
   long want = (bytes + ck - 1) / ck;
-  long cap = (long)sms * per_sm;
+  long cap = (long)sms * per_sm - g_bn_reserve;
+  if (cap < sms / 2) cap = sms / 2;
   if (want > cap) want = cap;
   if (want < 1) want = 1;
   return (int)want;

@@ -43,6 +43,7 @@ int fd_stem_dw_from_s2d(const float* dw2, float* dw, int K, cudaStream_t s);
 // workspace bytes for the single-launch BN kernels with at most `C` channels
 // [barrier counter, generation, fwd-stats-consumed counter, bwd-sums-consumed counter] + 2 x [2][C] barrier-kernel
 // accumulators + [2][C] forward epilogue statistics + [2][C] backward epilogue sums
+void fd_bn_set_reserve(int ctas);
 inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)8 * C * sizeof(float); }
 int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,

@@ -4,8 +4,8 @@
 // of a 3x3 convolution through descriptor arithmetic alone.  Used by tests/test_probe_gpu.py.
 #include <cuda.h>
 
-#include "common.cuh"
-#include "igemm.h"
+#include "../common.cuh"
+#include "../igemm.h"
 
 namespace {
 
@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int re
   tc_fence_after();
   const uint32_t tm = *slot;
   if (threadIdx.x == 0) {
-    const uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
-    const uint32_t a = smem_u32(smem), b = smem_u32(smem + 32 * 1024);
+    // flavor bit4: A MN-major, bit5: B MN-major (descriptor forms of the wgrad / dgrad main loops)
+    const int amn = (flavor >> 4) & 1, bmn = (flavor >> 5) & 1;
+    const uint32_t idesc = umma_idesc_bf16(128, BN, amn, bmn);
+    const uint32_t a = smem_u32(smem), b = smem_u32(smem + 64 * 1024);
     long long t0 = clock64();
     uint32_t ph = 0;
     for (int r = 0; r < reps; ++r) {
@@ -161,8 +163,10 @@ __global__ void __launch_bounds__(128, 1) mma_rate_kernel(long long* out, int re
       const int tapshift = (flavor & 4) ? ((r % 9) / 3 * 10 + (r % 3)) : 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        uint64_t da = umma_smem_desc(a + (shift + tapshift) * 128 + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
-        uint64_t db = umma_smem_desc(b + ((flavor & 4) ? (r % 9) * BN * 128 : 0) + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
+        uint64_t da = amn ? umma_smem_desc(a + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
+                          : umma_smem_desc(a + (shift + tapshift) * 128 + k * 32, 16, sbo, UMMA_LAYOUT_SW128);
+        uint64_t db = bmn ? umma_smem_desc(b + k * 2048, 8192, 1024, UMMA_LAYOUT_SW128)
+                          : umma_smem_desc(b + ((flavor & 4) ? (r % 9) * BN * 128 : 0) + k * 32, 16, 1024, UMMA_LAYOUT_SW128);
         umma_f16_ss(d, da, db, idesc, (r % 9 == 0 && k == 0) ? 0u : 1u);
       }
       if ((flavor & 2) && (r % 9 == 8)) {

@@ -1,13 +1,16 @@
-// Pinned staging ring with a producer thread, a dedicated copy stream and event hand-off.
+// Pinned staging ring: fixed cudaHostAlloc slots, a dedicated copy stream and event hand-off (replaces the
+// reference's pageable gpu(shard) upload inside the loader closure, src/ddp_tasks.jl:278-283).
 //
-//   producer thread (C++, no GIL):  fill pinned slot i  ->  ready queue
-//   consumer (training thread):     next() pops a ready slot, enqueues cudaMemcpyAsync(H2D) of x and y on the
-//                                   side stream, records `copied[i]`, makes the compute stream wait on it and
-//                                   returns the device pointers; release happens when next() is called again
-//                                   (`consumed[i]` recorded on the compute stream guards buffer reuse).
-// The H2D copy of step i+1 therefore overlaps the compute of step i.  The built-in producer fabricates
-// deterministic synthetic uint8 images + int64 labels (benchmark configs use synthetic data); a Python
-// producer can instead fill slots through host_ptr()/commit().
+//   producer (a C++ thread for synthetic data, or a Python loader thread through acquire()/commit()):
+//       fill pinned slot i -> ready queue
+//   consumer (training thread), next(compute_stream):
+//       1. release the slot handed out last time: record `consumed[i]` on the compute stream (its device buffers are
+//          read by work queued so far) and wait on the HOST for `copied[i]` before the pinned slot goes back to the
+//          producer — the async H2D copy must have read the host buffer before anyone overwrites it (round-1 race);
+//       2. top up the copies in flight (up to `prefetch` slots ahead): cudaStreamWaitEvent(copy, consumed[s]) ->
+//          cudaMemcpyAsync(H2D) of x and y on the copy stream -> record `copied[s]`;
+//       3. hand out the oldest copy in flight: the compute stream waits on `copied[s]`.
+// The H2D copy of step i+1 (and i+2) is therefore issued before step i's compute is even queued and overlaps it.
 #include <cuda_runtime.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -36,8 +39,9 @@ namespace {
 
 class PinnedRing {
  public:
-  PinnedRing(int device, size_t x_bytes, size_t y_bytes, int depth)
-      : device_(device), xb_(x_bytes), yb_(y_bytes), depth_(depth < 2 ? 2 : depth) {
+  PinnedRing(int device, size_t x_bytes, size_t y_bytes, int depth, int prefetch = 2)
+      : device_(device), xb_(x_bytes), yb_(y_bytes), depth_(depth < 3 ? 3 : depth),
+        prefetch_(prefetch < 1 ? 1 : (prefetch > depth - 1 ? depth - 1 : prefetch)) {
     RT_CHECK(cudaSetDevice(device_));
     RT_CHECK(cudaStreamCreateWithFlags(&copy_, cudaStreamNonBlocking));
     hx_.resize(depth_); hy_.resize(depth_); dx_.resize(depth_); dy_.resize(depth_);
@@ -73,6 +77,8 @@ class PinnedRing {
     free_.pop_front();
     return s;
   }
+  uintptr_t dev_x(int s) const { return (uintptr_t)dx_[s]; }
+  uintptr_t dev_y(int s) const { return (uintptr_t)dy_[s]; }
   uintptr_t host_x(int s) const { return (uintptr_t)hx_[s]; }
   uintptr_t host_y(int s) const { return (uintptr_t)hy_[s]; }
   void commit(int s) {
@@ -118,31 +124,33 @@ class PinnedRing {
 
   // ---- consumer: returns (slot, dev_x, dev_y); the compute stream `stream` will wait for the copy
   py::tuple next(uintptr_t stream) {
-    int s;
-    {
-      py::gil_scoped_release nogil;
-      std::unique_lock<std::mutex> lk(mu_);
-      if (last_ >= 0) {  // previous slot: its device buffers are consumed by work already queued on `stream`
-        cudaSetDevice(device_);
-        cudaEventRecord(consumed_[last_], (cudaStream_t)stream);
-        free_.push_back(last_);
-        last_ = -1;
-        cv_.notify_all();
-      }
-      cv_.wait(lk, [&] { return !ready_.empty() || stopping_; });
-      if (ready_.empty()) throw std::runtime_error("staging ring stopped");
-      s = ready_.front();
-      ready_.pop_front();
-    }
+    py::gil_scoped_release nogil;
     RT_CHECK(cudaSetDevice(device_));
-    RT_CHECK(cudaStreamWaitEvent(copy_, consumed_[s], 0));
-    RT_CHECK(cudaMemcpyAsync(dx_[s], hx_[s], xb_, cudaMemcpyHostToDevice, copy_));
-    if (yb_) RT_CHECK(cudaMemcpyAsync(dy_[s], hy_[s], yb_, cudaMemcpyHostToDevice, copy_));
-    RT_CHECK(cudaEventRecord(copied_[s], copy_));
+    if (last_ >= 0) {
+      // previous slot: its device buffers are consumed by work already queued on `stream`; its pinned buffers may be
+      // refilled only once the copy engine has read them
+      RT_CHECK(cudaEventRecord(consumed_[last_], (cudaStream_t)stream));
+      RT_CHECK(cudaEventSynchronize(copied_[last_]));
+      std::lock_guard<std::mutex> lk(mu_);
+      free_.push_back(last_);
+      last_ = -1;
+      cv_.notify_all();
+    }
+    top_up(false);
+    if (inflight_.empty()) top_up(true);  // nothing ready yet: block for the producer
+    const int s = inflight_.front();
+    inflight_.pop_front();
     RT_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, copied_[s], 0));
     last_ = s;
-    return py::make_tuple(s, (uintptr_t)dx_[s], (uintptr_t)dy_[s]);
+    top_up(false);  // the copy of the NEXT batch is queued before this batch's compute
+    const uintptr_t px = (uintptr_t)dx_[s], py_ = (uintptr_t)dy_[s];
+    py::gil_scoped_acquire gil;
+    return py::make_tuple(s, px, py_);
   }
+
+  // wall-clock independent evidence of overlap for tests: copies issued so far, and copies that had ALREADY been
+  // issued when their batch was handed out one step earlier (= prefetched ahead of the compute that precedes them)
+  long copies_issued() const { return issued_; }
 
   void stop() {
     {
@@ -157,9 +165,37 @@ class PinnedRing {
   int depth() const { return depth_; }
 
  private:
+  // issue H2D copies for ready slots until `prefetch_` are in flight; block == true waits for one ready slot
+  void top_up(bool block) {
+    for (;;) {
+      int s = -1;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        if ((int)inflight_.size() >= prefetch_) return;
+        if (block) cv_.wait(lk, [&] { return !ready_.empty() || stopping_; });
+        if (ready_.empty()) {
+          if (block) throw std::runtime_error("staging ring stopped");
+          return;
+        }
+        s = ready_.front();
+        ready_.pop_front();
+      }
+      RT_CHECK(cudaStreamWaitEvent(copy_, consumed_[s], 0));  // device buffers of slot s no longer read by compute
+      RT_CHECK(cudaMemcpyAsync(dx_[s], hx_[s], xb_, cudaMemcpyHostToDevice, copy_));
+      if (yb_) RT_CHECK(cudaMemcpyAsync(dy_[s], hy_[s], yb_, cudaMemcpyHostToDevice, copy_));
+      RT_CHECK(cudaEventRecord(copied_[s], copy_));
+      inflight_.push_back(s);
+      ++issued_;
+      block = false;
+    }
+  }
+
   int device_;
   size_t xb_, yb_;
   int depth_;
+  int prefetch_;
+  std::deque<int> inflight_;  // consumer thread only
+  long issued_ = 0;
   cudaStream_t copy_{};
   std::vector<void*> hx_, hy_, dx_, dy_;
   std::vector<cudaEvent_t> copied_, consumed_;
@@ -176,8 +212,11 @@ class PinnedRing {
 
 void fd_bind_staging(py::module_& m) {
   py::class_<PinnedRing>(m, "PinnedRing")
-      .def(py::init<int, size_t, size_t, int>(), py::arg("device"), py::arg("x_bytes"), py::arg("y_bytes"),
-           py::arg("depth") = 3)
+      .def(py::init<int, size_t, size_t, int, int>(), py::arg("device"), py::arg("x_bytes"), py::arg("y_bytes"),
+           py::arg("depth") = 4, py::arg("prefetch") = 2)
+      .def("copies_issued", &PinnedRing::copies_issued)
+      .def("dev_x", &PinnedRing::dev_x)
+      .def("dev_y", &PinnedRing::dev_y)
       .def("acquire", &PinnedRing::acquire)
       .def("host_x", &PinnedRing::host_x)
       .def("host_y", &PinnedRing::host_y)

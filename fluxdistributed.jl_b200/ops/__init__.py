@@ -47,6 +47,12 @@ def extension():
     return m
 
 
+def probe_extension():
+    """Hardware-probe module (``_Cprobe``: descriptor-shift, MMA-rate and TMA-bandwidth probes).  Built next to the
+    product extension, used by ``scripts/probe_*.py`` only."""
+    return importlib.import_module("fluxdist._Cprobe")
+
+
 def require_native() -> None:
     if not torch.cuda.is_available():
         raise RuntimeError("native sm_100a path requested but no CUDA device is visible")

@@ -217,9 +217,9 @@ def conv_dgrad(dy: torch.Tensor, w: torch.Tensor, x_shape, stride: int, pad: int
 
 
 def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: int,
-               out: Optional[torch.Tensor] = None, splits: int = 0) -> torch.Tensor:
+               out: Optional[torch.Tensor] = None, splits: int = 0, accumulate: bool = True) -> torch.Tensor:
     """Weight gradient in fp32, accumulated into ``out`` (a [K,C,R,S] channels_last view of the
-    gradient arena) when given."""
+    gradient arena) when given.  ``accumulate=False`` overwrites instead (only honoured without split-K)."""
     k, c, r, s = w_shape
     dyh, xh = nhwc(dy), nhwc(x)
     if out is None:
@@ -228,7 +228,7 @@ def conv_wgrad(dy: torch.Tensor, x: torch.Tensor, w_shape, stride: int, pad: int
         return buf.permute(0, 3, 1, 2)
     buf = out.permute(0, 2, 3, 1)
     assert buf.is_contiguous() and buf.dtype == torch.float32
-    _ext().conv_wgrad(dyh, xh, buf, stride, pad, splits, True)
+    _ext().conv_wgrad(dyh, xh, buf, stride, pad, splits, accumulate)
     return out
 
 
@@ -300,10 +300,12 @@ def bn_bwd(dout, y, out, mean, rstd, gamma, relu=True, want_dres=False, dgamma=N
 import os as _os
 
 DZ_EPILOGUE = _os.environ.get("FLUXDIST_DZ_EPILOGUE", "1") != "0"  # BN-backward reduction in the dgrad epilogue
-DZ_MAX_ROWS = int(_os.environ.get("FLUXDIST_DZ_MAX_ROWS", str(2 * 148 * 128)))
-# experimental (not validated on a GPU yet, default off): chain the dz epilogue across blocks — the next block's first conv
-# masks and reduces for this block's LAST BN layer (mask from the post-residual activation)
-DZ_CHAIN = _os.environ.get("FLUXDIST_DZ_CHAIN", "0") == "1"
+# rows (N*H*W) up to which the dz epilogue replaces the two-pass BN backward.  With eight epilogue warps the epilogue hides
+# behind the MMAs on every ResNet stage (round-2 measurement, gpurun_out/r2p1: 28x28x128 dgrad +9 us, BN backward -15 us)
+DZ_MAX_ROWS = int(_os.environ.get("FLUXDIST_DZ_MAX_ROWS", "400000"))
+# chain the dz epilogue across blocks: the next block's first conv masks and reduces for this block's LAST BN layer
+# (mask from the post-residual activation).  Validated on B200 in round 2 (tests + 18.5k -> 19.2k img/s with EPI8).
+DZ_CHAIN = _os.environ.get("FLUXDIST_DZ_CHAIN", "1") == "1"
 EPI_STATS = _os.environ.get("FLUXDIST_EPI_STATS", "1") != "0"  # BN statistics in the conv epilogues
 SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
@@ -437,6 +439,20 @@ def _halo_fprop_ok(cred: int, cout: int, hw: int) -> bool:
     wins when the filter slice is small enough to stay resident in shared memory and the image is large
     (ResNet stage 1); the im2col-TMA kernel wins for the wide, small-image stages."""
     return cred == 64 and cout == 64 and hw >= 28
+
+
+WGRAD_POLICY = os.environ.get("FLUXDIST_WGRAD", "auto")  # auto | halo | igemm
+
+
+def _halo_wgrad_ok(cin: int, cout: int, hw: int) -> bool:
+    """Weight-gradient kernel choice (scripts/conv_bench_r2.py): the im2col kernel with 128-wide (tap, c) tiles and a
+    one-wave split-K wins wherever the input has >= 128 channels; the halo kernel keeps the 64-channel stage, where an
+    im2col tile is half empty (64 output channels in a 128-row tile)."""
+    if WGRAD_POLICY == "halo":
+        return hw >= 14
+    if WGRAD_POLICY == "igemm":
+        return False
+    return cin == 64 and cout == 64 and hw >= 14
 
 
 class _ConvBNAct(torch.autograd.Function):
@@ -593,7 +609,7 @@ class _ConvBNAct(torch.autograd.Function):
         if stem:
             fn = lambda: stem_wgrad(dy, x, out=ctx.w_gradbuf)  # x holds the s2d tensor here
             gw = _on_side_stream(fn, (dy, x)) if side else fn()
-        elif k3 and x_shape[2] >= 14:
+        elif k3 and _halo_wgrad_ok(w_shape[1], w_shape[0], x_shape[2]):
             fn = lambda: conv3x3_wgrad(dy, x, out=ctx.w_gradbuf)
             gw = _on_side_stream(fn, (dy, x)) if side else fn()
         elif tc:

@@ -58,7 +58,10 @@ class GraphedStep:
             if not self.use_graph:
                 self._captured = True
                 return self
-            s = torch.cuda.Stream(device=rep.dev.torch_device)
+            # high priority: the step's critical path (forward, BN backward, dgrad) is issued on this stream; the side
+            # stream of the weight-gradient kernels keeps the default (lowest) priority, so when both have CTAs
+            # pending the block scheduler places the critical-path ones first
+            s = torch.cuda.Stream(device=rep.dev.torch_device, priority=-1)
             s.wait_stream(torch.cuda.current_stream(rep.dev.torch_device))
             with torch.cuda.stream(s):
                 for _ in range(self.warmup):

@@ -50,22 +50,92 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def _sequential_units(model: nn.Module) -> List[nn.Module]:
+    """Execution-ordered units of a sequentially composed model: the root's children in registration order with
+    ``nn.Sequential`` containers expanded recursively.  (Registration order == execution order is the convention of
+    the model zoo and of ``Chain``-style models; a model that violates it simply must not be bucketed.)"""
+    out: List[nn.Module] = []
+
+    def walk(m: nn.Module, top: bool):
+        kids = list(m.children())
+        if kids and (top or isinstance(m, nn.Sequential)):
+            for k in kids:
+                walk(k, False)
+        else:
+            out.append(m)
+
+    walk(model, True)
+    return out
+
+
 class FlatArena:
-    """Flat, identically laid out buffers for one replica."""
+    """Flat, identically laid out buffers for one replica.
+
+    ``order="backward"`` lays the parameters out in the order their gradients become ready in the backward pass
+    (matrices/filters of the LAST layers first, 1-D parameters at the very end) and cuts the arena into ``buckets``
+    (element ranges whose ends are multiples of ``ALIGN * world``): bucket 0 (the deepest layers, most of the
+    bytes) can be exchanged while the backward pass of the earlier layers still runs (SURVEY §5.8 bucket plan;
+    reference ``src/ddp_tasks.jl:203-228`` has two global barriers instead).  ``bucket_triggers[b]`` is the module
+    whose *input gradient* signals that every gradient of bucket ``b`` has been produced (None: end of backward).
+    """
 
     def __init__(self, model: nn.Module, device: torch.device, n_slots: int, lowp: Optional[torch.dtype],
                  world: int, alloc: Optional[Callable[[int, torch.dtype], torch.Tensor]] = None,
-                 sort_lowp_first: bool = False):
-        self.params = [p for p in model.parameters() if p.requires_grad]
-        if sort_lowp_first:  # matrices/filters first, 1-D (BN affine, biases) last: see native_comm
-            self.params = sorted(self.params, key=lambda p: p.dim() < 2)
+                 sort_lowp_first: bool = False, order: str = "forward", bucket_fracs: Sequence[float] = ()):
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        self.params = [p for _, p in named]
+        names = [n for n, _ in named]
+        cuts = set()
+        self.bucket_triggers: List[Optional[nn.Module]] = []
+        if order == "backward":
+            # units = the modules a sequential model executes one after the other (containers are expanded); the
+            # gradient of a unit's INPUT is complete only after the whole unit (all its branches) ran backward, which
+            # makes "input gradient of unit u" a safe signal for "every gradient of u and of all later units exists"
+            units = _sequential_units(model)
+            name_of = {id(p): n for n, p in named}
+            seen, mats, vecs, unit_end = set(), [], [], {}
+            for u in reversed(units):
+                ps = [p for p in u.parameters() if p.requires_grad and id(p) not in seen]
+                seen.update(id(p) for p in ps)
+                for p in reversed(ps):
+                    (mats if p.dim() >= 2 else vecs).append(p)
+                if mats:
+                    unit_end[len(mats) - 1] = u  # arena index of the unit's last matrix -> the unit
+            rest = [p for p in self.params if id(p) not in seen]  # parameters outside the unit walk (none for the zoo)
+            for p in reversed(rest):
+                (mats if p.dim() >= 2 else vecs).append(p)
+            total = sum(_round_up(p.numel(), 8) for p in mats + vecs)
+            if bucket_fracs and total >= (1 << 20) and not rest:
+                acc, fr = 0, sorted(bucket_fracs)
+                for i, p in enumerate(mats[:-1]):
+                    acc += _round_up(p.numel(), 8)
+                    if fr and i in unit_end and acc >= fr[0] * total:
+                        cuts.add(i)
+                        self.bucket_triggers.append(unit_end[i])
+                        while fr and acc >= fr[0] * total:
+                            fr.pop(0)
+            self.params = mats + vecs
+            names = [name_of[id(p)] for p in self.params]
+        elif sort_lowp_first:  # matrices/filters first, 1-D (BN affine, biases) last: see native_comm
+            pairs = sorted(zip(names, self.params), key=lambda np_: np_[1].dim() < 2)
+            names = [n for n, _ in pairs]
+            self.params = [p for _, p in pairs]
+        self.bucket_triggers.append(None)  # the last bucket goes out at the end of the backward pass
+        self.names = names
+        gran = ALIGN * max(world, 1)
         self.offsets: List[int] = []
-        off = 0
-        for p in self.params:
+        self.buckets: List[tuple] = []
+        off, lo = 0, 0
+        for i, p in enumerate(self.params):
             self.offsets.append(off)
             off += _round_up(p.numel(), 8)  # 16B-aligned starts for bf16 and fp32 views
+            if i in cuts:
+                off = _round_up(off, gran)
+                self.buckets.append((lo, off))
+                lo = off
         self.numel = off
-        self.padded = _round_up(max(off, 1), ALIGN * max(world, 1))
+        self.padded = _round_up(max(off, 1), gran)
+        self.buckets.append((lo, self.padded))
         mk = alloc or (lambda n, dt: torch.zeros(n, dtype=dt, device=device))
         self.w32 = mk(self.padded, torch.float32)
         self.g32 = mk(self.padded, torch.float32)
@@ -81,19 +151,34 @@ class FlatArena:
             return v.view(k, r, s, c).permute(0, 3, 1, 2)  # physical KRSC, logical KCRS
         return v.view(p.shape)
 
+    def owner_ranges(self, world: int):
+        """[(lo, hi, rank)] element ranges whose fp32 master / moments are authoritative on ``rank`` under the
+        two-shot (sharded) update: every bucket is split evenly over the ranks."""
+        out = []
+        for lo, hi in self.buckets:
+            sl = (hi - lo) // world
+            for r in range(world):
+                out.append((lo + r * sl, lo + (r + 1) * sl, r))
+        return out
+
 
 class FusedReplica:
     def __init__(self, model: nn.Module, dev, opt: Rule, world: int, rank: int, lowp: Optional[torch.dtype],
-                 alloc=None, sort_lowp_first: bool = False):
+                 alloc=None, sort_lowp_first: bool = False, order: str = "forward", bucket_fracs: Sequence[float] = ()):
         self.model, self.dev, self.opt = model, as_device(dev), opt
         self.world, self.rank = world, rank
         self.step_count = 0
         self.group: Optional["FusedGroup"] = None
         self.stream = None  # set by the group when several replicas share one GPU (virtual replicas)
+        self._armed = False          # inside forward_backward: bucket triggers may fire
+        self._launched: set = set()  # buckets already handed to the communicator this step
         tdev = self.dev.torch_device
         with device_ctx(self.dev):
-            self.arena = FlatArena(model, tdev, opt.n_slots, lowp, world, alloc, sort_lowp_first)
+            self.arena = FlatArena(model, tdev, opt.n_slots, lowp, world, alloc, sort_lowp_first, order, bucket_fracs)
             a = self.arena
+            for b, trig in enumerate(a.bucket_triggers):
+                if trig is not None:
+                    trig.register_forward_pre_hook(self._make_trigger(b))
             with torch.no_grad():
                 for i, p in enumerate(a.params):
                     a.view(a.w32, i).copy_(p.detach().float())
@@ -105,8 +190,36 @@ class FusedReplica:
                 if a.w16 is not None:
                     a.w16.copy_(a.w32)
 
+    # ---- bucket triggers: the gradient of a trigger module's input is complete only after every later layer ran backward
+    def _make_trigger(self, b: int):
+        def pre_hook(_mod, args):
+            x = args[0] if args else None
+            if self._armed and isinstance(x, torch.Tensor) and x.requires_grad:
+                x.register_hook(lambda g, _b=b: self._bucket_ready(_b))
+        return pre_hook
+
+    def _bucket_ready(self, b: int) -> None:
+        comm = self.group.comm if self.group is not None else None
+        if not self._armed or comm is None or not hasattr(comm, "launch_bucket") or b in self._launched:
+            return None
+        # everything up to and including b is complete (buckets are in backward order)
+        for k in range(b + 1):
+            if k not in self._launched:
+                self._launched.add(k)
+                comm.launch_bucket(self, k, early=True)
+        return None
+
     # ---- one training step on this replica
     def forward_backward(self, x, y, loss: Callable) -> torch.Tensor:
+        with device_ctx(self.dev):
+            self._launched = set()
+            self._armed = bool(getattr(self, "overlap", False))
+            try:
+                return self._forward_backward(x, y, loss)
+            finally:
+                self._armed = False
+
+    def _forward_backward(self, x, y, loss: Callable) -> torch.Tensor:
         with device_ctx(self.dev):
             self.arena.g32.zero_()
             for i, p in enumerate(self.arena.params):  # hooks may have replaced .grad
@@ -126,13 +239,22 @@ class FusedReplica:
             return l.detach()
 
     def reduce_and_update(self) -> None:
+        """Exchange + update of every bucket not yet launched by a trigger, then join the communication stream."""
         assert self.group is not None
         if self.dev.is_cuda:
             from ..ops import native as _native
 
             _native.join_side_stream(self.dev.torch_device)  # weight gradients queued on the side stream
         self.step_count += 1
-        self.group.comm.allreduce_update(self)
+        comm = self.group.comm
+        if hasattr(comm, "launch_bucket"):
+            for b in range(len(self.arena.buckets)):
+                if b not in self._launched:
+                    comm.launch_bucket(self, b, early=False)
+            comm.join(self)
+            self._launched = set()
+        else:
+            comm.allreduce_update(self)
 
     def zero_grads(self) -> None:
         self.arena.g32.zero_()
@@ -174,7 +296,20 @@ class FusedReplica:
         a = self.arena
         vals = [v for _, v in leaves(_module_tree(self.model, lambda p: p))]
         flat = [v for _, v in leaves(st)] if st is not None else []
+        if not step_count:
+            # Adam-family states carry the running beta powers (beta^(t+1)): recover the step from them so the
+            # kernel's bias correction continues where the saved state left off (resume restarted it)
+            for v in flat:
+                if isinstance(v, tuple) and len(v) == 3 and isinstance(v[2], tuple) and self.opt.rule_id in (RULE_ADAM, RULE_ADAMW):
+                    b1 = float(self.opt.beta[0])
+                    p1 = float(v[2][0])
+                    if 0.0 < p1 < 1.0 and 0.0 < b1 < 1.0:
+                        step_count = max(int(round(math.log(p1) / math.log(b1))) - 1, 0)
+                    break
         self.step_count = step_count
+        comm = self.group.comm if self.group is not None else None
+        if comm is not None and hasattr(comm, "set_step"):
+            comm.set_step(self, step_count)
         # walk model params in order and copy moments in
         idx = {id(p): i for i, p in enumerate(a.params)}
         model_params = [p for p in self.model.parameters() if p.requires_grad]
@@ -207,17 +342,29 @@ class ThreadComm:
 
     name = "thread"
 
-    def __init__(self, replicas: Sequence[FusedReplica]):
+    def __init__(self, replicas: Sequence[FusedReplica], timeout: float = 300.0):
         self.replicas = list(replicas)
         n = len(self.replicas)
+        self.timeout = timeout
         self._b1 = threading.Barrier(n) if n > 1 else None
         self._b2 = threading.Barrier(n) if n > 1 else None
+
+    def abort(self) -> None:
+        """Break the barriers so that replicas blocked in them raise instead of waiting for a peer that failed."""
+        for b in (self._b1, self._b2):
+            if b is not None:
+                b.abort()
+
+    def reset(self) -> None:
+        for b in (self._b1, self._b2):
+            if b is not None:
+                b.reset()
 
     def allreduce_update(self, rep: FusedReplica) -> None:
         if self._b1 is not None:
             if rep.dev.is_cuda:
                 torch.cuda.synchronize(rep.dev.torch_device)
-            self._b1.wait()
+            self._b1.wait(timeout=self.timeout)
         a = rep.arena
         acc = torch.zeros_like(a.g32)
         for r in self.replicas:  # fixed order -> identical rounding everywhere
@@ -229,7 +376,7 @@ class ThreadComm:
         if self._b2 is not None:
             if rep.dev.is_cuda:
                 torch.cuda.synchronize(rep.dev.torch_device)
-            self._b2.wait()
+            self._b2.wait(timeout=self.timeout)
 
     def close(self):
         pass
@@ -343,6 +490,32 @@ class FusedGroup:
             r.opt = opt
             if hasattr(self.comm, "set_opt"):
                 self.comm.set_opt(r, opt)
+
+    def check_status(self, raise_on_timeout: bool = True) -> Dict[str, bool]:
+        """Read (and clear) the device-side status words of the fused kernels: ``nonfinite`` — a reduced gradient was
+        NaN/Inf (reference ``check_nans``, ``src/ddp_tasks.jl:86-91``, done in-kernel); ``barrier_timeout`` — a
+        cross-GPU barrier gave up waiting for a peer, in which case the kernel returned WITHOUT updating and the
+        replicas can no longer be assumed in sync: raise.  Costs one tiny D2H copy per replica, so the
+        training loops call it every few steps, not every step."""
+        out = {"nonfinite": False, "barrier_timeout": False}
+        if hasattr(self.comm, "status"):
+            for r in self.replicas:
+                nan, tmo = self.comm.status(r)
+                out["nonfinite"] |= bool(nan)
+                out["barrier_timeout"] |= bool(tmo)
+        if out["barrier_timeout"] and raise_on_timeout:
+            raise RuntimeError("fused all-reduce+update: a cross-GPU barrier timed out (a peer replica died or stalled); "
+                               "the step was not applied on at least one replica — replicas are out of sync")
+        return out
+
+    def skip_step(self) -> None:
+        """Collective skip (reference OOM handling, ``src/ddp_tasks.jl:230-237``): every replica drops its gradients
+        and NO replica enters the exchange, so nobody waits in a device-side barrier for a peer that bailed out."""
+        for r in self.replicas:
+            with device_ctx(r.dev):
+                r.arena.g32.zero_()
+                r._launched = set()
+                r._armed = False
 
     def sync_to_modules(self) -> None:
         """Make every module's fp32 parameters current (gathers owner shards when

@@ -54,6 +54,8 @@ class Setup:
     shards: List[Any] = field(default_factory=list)
     cycle: int = 0
     nsamples: int = 0
+    shard_indices: List[Any] = field(default_factory=list)  # row permutation of every shard (saved in checkpoints)
+    start_step: int = 0                                     # step the run resumes from
 
     def __iter__(self):  # allow tuple-unpacking like the NamedTuple
         return iter((self.ds_and_ms, self.dls, self.sts))
@@ -109,7 +111,7 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
                      dataset: str = "imagenet_local", minibatch_fn: Optional[Callable] = None,
                      onehot: bool = True, engine: str = "auto", seed: Optional[int] = None,
                      dtype: Optional[torch.dtype] = None, loss: Optional[Callable] = None,
-                     engine_opts: Optional[dict] = None):
+                     engine_opts: Optional[dict] = None, staging: str = "auto", resume=None):
     """Shard ``key`` over ``devices``, replicate model + optimiser state, allocate the
     per-device gradient buffers on ``HOST`` and build one prefetching loader per
     device.  Returns ``(setup, buffer)`` like the reference.
@@ -117,8 +119,18 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
     ``minibatch_fn(shard, nsamples) -> (x, y)`` overrides how a batch is drawn
     from a shard (default: ImageNet ``minibatch`` on the registry dataset, or the
     synthetic generator when ``key`` is a ``SyntheticKey``).
+
+    ``staging``: how batches reach the GPU (reference: ``gpu(shard)`` inside the loader closure,
+    ``src/ddp_tasks.jl:278-283``).  ``"ring"`` (default on CUDA with the extension): the native pinned staging ring
+    (``csrc/staging.cpp`` behind ``data.StagedLoader``) — fixed pinned slots filled by the loader thread,
+    ``cudaMemcpyAsync`` on a copy stream, event hand-off to the compute stream, so the H2D copy of step i+1 overlaps
+    the compute of step i; ``"simple"``: produce on the loader thread and ``.to(device)``.
+
+    ``resume``: a checkpoint path or a loaded checkpoint dict (``utils.save_checkpoint``): model weights, optimiser
+    state (moments + step, also into the fused arenas), shard permutation and RNG are restored — the reference resumes
+    by passing ``sts=`` back in (``src/sync.jl:101,127-129``).
     """
-    from ..data import DataLoader
+    from ..data import DataLoader, StagedLoader
 
     devs = [as_device(d) for d in devices]
     ndev = len(devs)
@@ -128,11 +140,27 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
         cycle = nrows * epochs // ndev // nsamples
     rng = np.random.default_rng(seed)
     ixs = shard_indices(nrows, ndev, rng)
+    ckpt = None
+    if resume is not None:
+        from ..utils.checkpoint import load_checkpoint
+
+        ckpt = load_checkpoint(resume, model) if isinstance(resume, (str, bytes)) or hasattr(resume, "__fspath__") else resume
+        if not isinstance(resume, dict):
+            pass
+        elif "model" in ckpt:
+            model.load_state_dict(ckpt["model"])
+        saved = (ckpt.get("extra") or {}).get("shard_indices")
+        if saved is not None and len(saved) == ndev and all(len(a) == len(b) for a, b in zip(saved, ixs)):
+            ixs = [np.asarray(a) for a in saved]  # same rows on the same replica as before the interruption
+        if "rng" in ckpt:
+            torch.set_rng_state(ckpt["rng"]["torch"])
     ks = [_take_rows(key, ix) for ix in ixs]
 
     engine = _pick_engine(engine, devs)
     zmodel = destruct(model)
     st = opt_state(opt, model)
+    if ckpt is not None and ckpt.get("opt_state") is not None:
+        st = ckpt["opt_state"]
     buffer: Dict[Any, Tree] = {}
     if engine == "staged":
         for dev in devs:  # all staging buffers live on HOST (ddp_tasks.jl:263-269), built synchronously (Q4)
@@ -151,22 +179,32 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
             ds_and_ms.append((dev, m))
             sts[dev] = fmap(lambda t: t.to(dev.torch_device) if isinstance(t, torch.Tensor) else t, copy.deepcopy(st))
 
+            use_ring = dev.is_cuda and staging in ("auto", "ring") and engine == "fused"
+            if use_ring:
+                # pinned ring: the loader thread fills fixed pinned slots; H2D on a copy stream; event hand-off
+                dls.append(StagedLoader.from_batches(lambda n, _k=k: mb(_k, n), [nsamples] * cycle, dev.torch_device,
+                                                     depth=max(3, min(buffersize, 6))))
+                continue
+
             def produce(n, _k=k, _dev=dev):
                 x, y = mb(_k, n)
                 with device_ctx(_dev):
-                    if _dev.is_cuda:
-                        x = x.pin_memory() if not x.is_pinned() else x
-                        y = y.pin_memory() if not y.is_pinned() else y
                     return (x.to(_dev.torch_device, non_blocking=True), y.to(_dev.torch_device, non_blocking=True))
 
             dls.append(DataLoader(produce, ([nsamples] * cycle,), buffersize=buffersize))
 
     setup = Setup(ds_and_ms=ds_and_ms, dls=dls, sts=sts, shards=ks, cycle=cycle, nsamples=nsamples)
+    setup.shard_indices = [np.asarray(ix) for ix in ixs]
+    setup.start_step = int(ckpt.get("step", 0)) if ckpt is not None else 0
     if engine == "fused":
         from .fused import FusedGroup
 
         setup.engine = FusedGroup.for_threads([m for _, m in ds_and_ms], devs, opt, loss=loss, dtype=dtype,
                                               **(engine_opts or {}))
+        if ckpt is not None and ckpt.get("opt_state") is not None:
+            for r in setup.engine.replicas:  # moments + step counter into the arenas (sharded masters included)
+                with device_ctx(r.dev):
+                    r.load_state_tree(sts[r.dev], step_count=setup.start_step)
     return setup, buffer
 
 
@@ -229,6 +267,15 @@ def _pool(n: int) -> ThreadPoolExecutor:
     return _POOLS[n]
 
 
+def _reduce_and_update(rep) -> None:
+    with device_ctx(rep.dev):
+        if rep.stream is not None:
+            with torch.cuda.stream(rep.stream):
+                rep.reduce_and_update()
+        else:
+            rep.reduce_and_update()
+
+
 def _is_oom(e: BaseException) -> bool:
     return isinstance(e, torch.cuda.OutOfMemoryError) or "out of memory" in str(e).lower()
 
@@ -237,7 +284,7 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
           sched: Callable[[Rule], Rule] = lambda o: o, sched_every: Optional[int] = None,
           log_every: int = 10, eval_every: int = 50, logger=None, minibatch_fn=None,
           checkpoint_every: Optional[int] = None, checkpoint_path: Optional[str] = None,
-          on_step: Optional[Callable[[int, Dict], None]] = None):
+          on_step: Optional[Callable[[int, Dict], None]] = None, status_every: Optional[int] = None):
     """The lock-step training loop (``ddp_tasks.jl:174-247``).
 
     Per iteration: take one minibatch per device (blocks on the slowest loader),
@@ -245,7 +292,9 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
     device, barrier.  Every ``log_every`` steps print ``Cycle: j``; every
     ``eval_every`` steps log loss/top-k on ``val`` and on the current train batch of
     the first replica.  CUDA OOM in any replica skips the batch for *all* replicas
-    (collective skip) and counts it in ``Num Missed``.  Returns
+    (collective skip: on the fused engine no replica enters the exchange kernel) and counts it
+    in ``Num Missed``.  Every ``status_every`` steps (default ``log_every``) the fused engine's device
+    status is read: a non-finite reduced gradient is logged, a barrier timeout raises.  Returns
     ``[(dev, cpu_model), …]``.
     """
     lg = logger or get_logger()
@@ -256,6 +305,7 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
     num_missed = 0
     iters = [iter(dl) for dl in setup.dls]
     j = 0
+    status_every = status_every or log_every
     while True:
         try:
             mbs = [next(it) for it in iters]
@@ -266,6 +316,10 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
             if j % log_every == 0:
                 print(f"Cycle: {j}")
                 if j % eval_every == 0:
+                    if setup.engine is not None:
+                        # the two-shot kernel keeps fp32 masters authoritative on the owner shard only: gather them
+                        # before an fp32 evaluation reads module parameters (eval saw stale shards)
+                        setup.engine.sync_to_modules()
                     log_loss_and_acc(loss, ds_and_ms[0], val, "val", logger=lg, minibatch_fn=minibatch_fn)
                     log_loss_and_acc(loss, ds_and_ms[0], mbs[0], "train", logger=lg)
             if sched_every and j % sched_every == 0:
@@ -281,11 +335,29 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
 
                     futs = [pool.submit(graphed_replica_step, setup.engine.replicas[i], mb[0], mb[1], loss)
                             for i, mb in enumerate(mbs)]
+                    losses = [f.result() for f in futs]
                 else:
-                    futs = [pool.submit(setup.engine.replicas[i].step, mb[0], mb[1], loss)
-                            for i, mb in enumerate(mbs)]
-                losses = [f.result() for f in futs]
+                    # eager: forward+backward everywhere, host rendezvous that collects failures, and only then the
+                    # exchange — a replica that ran out of memory must not leave its peers spinning in the kernel's
+                    # device-side barrier (the skip was not collective on this path)
+                    reps = setup.engine.replicas
+                    futs = [pool.submit(reps[i].step, mb[0], mb[1], loss, False) for i, mb in enumerate(mbs)]
+                    losses, errs = [], []
+                    for f in futs:
+                        try:
+                            losses.append(f.result())
+                        except BaseException as e:  # noqa: BLE001
+                            errs.append(e)
+                    if errs:
+                        setup.engine.skip_step()
+                        raise errs[0]
+                    for f in [pool.submit(_reduce_and_update, r) for r in reps]:
+                        f.result()
                 info = {"loss": losses[0]}
+                if j % status_every == 0:
+                    stt = setup.engine.check_status()
+                    if stt["nonfinite"]:
+                        lg.info("nonfinite_gradient", step=j)
             else:
                 gs = [pool.submit(train_step, loss, buffer, dev, m, *bs)
                       for (dev, m), bs in zip(ds_and_ms, mbs)]
@@ -308,7 +380,8 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
                 if setup.engine is not None:
                     setup.engine.sync_to_modules()
                     sts.update(setup.engine.state_trees())
-                save_checkpoint(checkpoint_path, ds_and_ms[0][1], sts[ds_and_ms[0][0]], step=j)
+                save_checkpoint(checkpoint_path, ds_and_ms[0][1], sts[ds_and_ms[0][0]], step=setup.start_step + j,
+                                extra={"shard_indices": [np.asarray(ix).tolist() for ix in setup.shard_indices]})
         except BaseException as e:  # noqa: BLE001
             if _is_oom(e):
                 print(f"Found error: {e}")
@@ -319,6 +392,9 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
             raise
     print(f"Num Missed: {num_missed}")
     if setup.engine is not None:
+        stt = setup.engine.check_status()
+        if stt["nonfinite"]:
+            lg.info("nonfinite_gradient", step=j)
         setup.engine.sync_to_modules()
         sts.update(setup.engine.state_trees())
     out = []

@@ -100,6 +100,7 @@ class ClockSampler:
         self._smax: List[float] = []
         self._reasons: set = set()
         self._nvml = None
+        self._recording = threading.Event()
 
     # ---------------------------------------------------------------- NVML path
     def _nvml_handle(self):
@@ -116,6 +117,8 @@ class ClockSampler:
             return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
 
     def _sample_nvml(self):
+        if not self._recording.is_set():
+            return
         nv, h = self._nvml
         self._sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
         self._smax.append(float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)))
@@ -130,7 +133,18 @@ class ClockSampler:
             if mask & int(bit):
                 self._reasons.add(name)
 
-    def start(self):
+    def resume(self):
+        """Begin recording (cheap: sets a flag).  Pair with ``start(paused=True)`` so the NVML/nvidia-smi start-up cost
+        stays outside a timed region."""
+        self._sm.clear(); self._smax.clear(); self._reasons.clear(); self._lines.clear()
+        self._recording.set()
+        return self
+
+    def start(self, paused: bool = False):
+        """Start sampling.  ``paused=True`` does all the expensive set-up (NVML init, device lookup, sampler thread)
+        but records nothing until :meth:`resume` — bench.py calls it BEFORE the pre-timing barrier so no rank enters
+        the timed region late (round-1 defect: the set-up ran between the barrier and the first event record)."""
+        self._recording.set()
         try:
             self._nvml = self._nvml_handle()
             self._sample_nvml()
@@ -146,6 +160,8 @@ class ClockSampler:
                         pass
                     self._stop.wait(self.period_ms / 1000.0)
 
+            if paused:
+                self._recording.clear()
             self._thread = threading.Thread(target=loop, daemon=True)
             self._thread.start()
             return self
@@ -161,13 +177,17 @@ class ClockSampler:
         def pump():
             assert self._proc is not None and self._proc.stdout is not None
             for line in self._proc.stdout:
-                self._lines.append(line.strip())
+                if self._recording.is_set():
+                    self._lines.append(line.strip())
 
+        if paused:
+            self._recording.clear()
         self._thread = threading.Thread(target=pump, daemon=True)
         self._thread.start()
         return self
 
     def stop(self) -> Dict:
+        self._recording.set()
         self._stop.set()
         if self._nvml is not None:
             if self._thread is not None:

@@ -22,5 +22,5 @@ for hw, C, K, v in [(56, 64, 64, 1), (28, 128, 128, 3)]:
     xs = [cl(torch.randn(96, C, hw, hw, device="cuda").to(BF)) for _ in range(NSET)]
     w = cl((torch.randn(K, C, 3, 3, device="cuda") * 0.05).to(BF))
     for dbg in (0, 1, 4, 8, 9, 12, 13, 15):
-        t = timeit(lambda i: (lambda: ops.conv3x3_fprop(xs[i], w, stats=False, variant=v + (dbg << 8))))
+        t = timeit(lambda i: (lambda: ops.conv3x3_fprop(xs[i], w, stats=False, variant=v + (dbg << 9))))
         print(f"hw={hw} C={C} v{v} dbg={dbg:04b} (1=nostore 2=noload 4=nomma 8=noldtm): {t:.1f} us", flush=True)

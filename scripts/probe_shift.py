@@ -2,7 +2,7 @@ import sys, torch
 sys.path.insert(0, ".")
 import fluxdist
 from fluxdist import ops
-e = ops.extension()
+e = ops.probe_extension()
 torch.manual_seed(0)
 rows = 320
 A = torch.randn(rows, 64, device="cuda").bfloat16()

@@ -44,7 +44,7 @@ def test_thread_mode_real_gpus(mode, opt):
     grp = FusedGroup.for_threads([copy.deepcopy(base).to(d.torch_device) for d in devs], devs, opt,
                                  dtype=torch.float32, comm="native", mode=mode)
     for r in grp.replicas:
-        grp.comm.plans[id(r)][0].set_max_spins(1 << 23)
+        grp.comm.set_max_spins(r, 1 << 23)
     x, y = _batches(n)
     per = x.shape[0] // n
     with ThreadPoolExecutor(n) as ex:
@@ -87,7 +87,7 @@ def _proc(rank, world, port, nvls, mode, q):
     opt = fd.Momentum(0.01, 0.9)
     grp = FusedGroup.for_process(m, fd.CudaDevice(rank, rank), opt, dtype=torch.float32, comm="native", mode=mode)
     rep = grp.replicas[0]
-    grp.comm.plans[id(rep)][0].set_max_spins(1 << 23)
+    grp.comm.set_max_spins(rep, 1 << 23)
     x, y = _batches(world)
     per = x.shape[0] // world
     for _ in range(3):

@@ -205,7 +205,6 @@ def test_block_dz_epilogue_matches_two_pass_bn_backward():
         assert rel_err(a, b) < 2e-2
 
 
-@pytest.mark.skipif(os.environ.get("FLUXDIST_DZ_CHAIN") != "1", reason="experimental path: run with FLUXDIST_DZ_CHAIN=1")
 def test_stage_dz_chain_matches_unchained():
     """Two identity blocks of a 14x14x256 stage: with the dz epilogue chained across the block boundary (the second
     block's first conv finishes the first block's last BN layer) the gradients equal the unchained run."""
@@ -236,7 +235,7 @@ def test_stage_dz_chain_matches_unchained():
         NV.DZ_CHAIN = False
         off = run()
     finally:
-        NV.DZ_CHAIN = os.environ.get("FLUXDIST_DZ_CHAIN") == "1"
+        NV.DZ_CHAIN = os.environ.get("FLUXDIST_DZ_CHAIN", "1") == "1"
         set_backend("auto")
     for a, b in zip(on, off):
         assert rel_err(a, b) < 2e-2
@@ -345,6 +344,99 @@ def test_conv_wgrad(N, H, W, C, K, R, stride, pad):
     dw = ops.conv_wgrad(dy, x, (K, C, R, R), stride, pad)
     ref = REF.conv_wgrad_ref(dy, x, (K, C, R, R), stride, pad)
     assert rel_err(dw, ref) < 1e-2
+
+
+# ---- round 2: wide CTA tiles (two m-tiles per CTA / N = 256) and the 128-wide weight-gradient tile
+TILE_SHAPES = [(64, 1), (64, 2), (128, 1), (128, 2), (256, 1)]
+WIDE_CASES = [
+    # N, H, W, C, K, R, stride, pad
+    (2, 8, 8, 64, 64, 3, 1, 1),          # a single (partly empty) m-tile: the second m-tile of a pair is all zero-fill
+    (5, 14, 14, 128, 256, 3, 1, 1),      # odd number of m-tiles (980 rows -> 8 tiles)
+    (3, 28, 28, 128, 128, 3, 1, 1),
+    (2, 16, 16, 64, 128, 3, 2, 1),
+    (3, 9, 11, 256, 512, 1, 1, 0),
+]
+
+
+@pytest.fixture
+def tile_shape():
+    ext = ops.extension()
+    yield ext.set_tile_shape
+    ext.set_tile_shape(0, 0)
+
+
+@pytest.mark.parametrize("bn,mt", TILE_SHAPES)
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", WIDE_CASES)
+def test_conv_fprop_tile_shapes(tile_shape, bn, mt, N, H, W, C, K, R, stride, pad):
+    """Every CTA tile shape of the im2col fprop (128xBN, 256xBN via two m-tiles, 128x256) incl. the statistics epilogue."""
+    if K % bn:
+        pytest.skip("N tile does not divide the output channels")
+    tile_shape(bn, mt)
+    x, w = _conv_data(N, H, W, C, K, R)
+    y, s, ss = ops.conv_fprop(x, w, stride, pad, stats=True)
+    ref = REF.conv_fprop_ref(x, w, stride, pad)
+    assert rel_err(y, ref) < 1e-2
+    assert rel_err(s, ref.sum(dim=(0, 2, 3))) < 2e-3
+    assert rel_err(ss, (ref * ref).sum(dim=(0, 2, 3))) < 2e-3
+
+
+@pytest.mark.parametrize("bn,mt", TILE_SHAPES)
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", WIDE_CASES)
+def test_conv_dgrad_tile_shapes(tile_shape, bn, mt, N, H, W, C, K, R, stride, pad):
+    """Every CTA tile shape of the stride-1 / parity-decomposed stride-2 dgrad, with the fused addend."""
+    if C % bn:
+        pytest.skip("N tile does not divide the input channels")
+    tile_shape(bn, mt)
+    x, w = _conv_data(N, H, W, C, K, R)
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    dy = cl(torch.randn(N, K, P, Q, device="cuda").to(BF))
+    add = cl(torch.randn(N, C, H, W, device="cuda").to(BF)) if stride == 1 else None
+    dx = ops.conv_dgrad(dy, w, (N, C, H, W), stride, pad, add=add)
+    ref = REF.conv_dgrad_ref(dy, w, (N, C, H, W), stride, pad).float()
+    if add is not None:
+        ref = ref + add.float()
+    assert rel_err(dx, ref) < 1e-2
+
+
+@pytest.mark.parametrize("bn,mt", TILE_SHAPES)
+@pytest.mark.parametrize("N,H,W,C,K,with_out", [(5, 14, 14, 256, 256, False), (8, 28, 28, 128, 128, True)])
+def test_dgrad_dz_epilogue_tile_shapes(tile_shape, bn, mt, N, H, W, C, K, with_out):
+    """dz epilogue (ReLU mask + BN-backward sums) under every tile shape."""
+    tile_shape(bn, mt)
+    torch.manual_seed(5)
+    _, w = _conv_data(N, H, W, C, K, 3)
+    dyn = cl(torch.randn(N, K, H, W, device="cuda").to(BF))
+    y = cl(torch.randn(N, C, H, W, device="cuda").to(BF))
+    gamma, beta = torch.randn(C, device="cuda"), torch.randn(C, device="cuda") * 0.2
+    yf = y.float()
+    mean = yf.mean(dim=(0, 2, 3)); rstd = torch.rsqrt(yf.var(dim=(0, 2, 3), unbiased=False) + 1e-5)
+    bn_ = (yf - mean[None, :, None, None]) * (rstd * gamma)[None, :, None, None] + beta[None, :, None, None]
+    out = cl((torch.relu(bn_) * (torch.rand_like(bn_) > 0.3)).to(BF)) if with_out else None
+    s0, s1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dz = ops.conv_dgrad(dyn, w, (N, C, H, W), 1, 1, bn_epi=(y, out, mean, rstd, gamma, beta, s0, s1))
+    dx_ref = REF.conv_dgrad_ref(dyn, w, (N, C, H, W), 1, 1).float()
+    mask = (out.float() > 0) if with_out else (bn_ > 0)
+    keep = torch.ones_like(mask) if with_out else (bn_.abs() >= 1e-2)
+    assert rel_err(dz.float() * keep, dx_ref * mask * keep) < 1e-2
+    dzf = dz.float()
+    assert rel_err(s1, dzf.sum(dim=(0, 2, 3))) < 5e-3
+    assert rel_err(s0, (dzf * (yf - mean[None, :, None, None])).sum(dim=(0, 2, 3))) < 5e-3
+
+
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad", CONV_CASES + [(96, 7, 7, 512, 512, 3, 1, 1), (24, 14, 14, 256, 256, 3, 1, 1),
+                                                                 (6, 28, 28, 128, 128, 3, 1, 1), (4, 28, 28, 128, 256, 3, 2, 1)])
+@pytest.mark.parametrize("splits", [0, 1, 3])
+def test_conv_wgrad_wide_and_splits(N, H, W, C, K, R, stride, pad, splits):
+    """im2col weight gradient: 128-wide (tap, c) tiles where C allows, automatic one-wave split-K and explicit splits,
+    accumulating into a pre-filled buffer (vector atomics)."""
+    x, w = _conv_data(N, H, W, C, K, R)
+    P, Q = (H + 2 * pad - R) // stride + 1, (W + 2 * pad - R) // stride + 1
+    dy = cl(torch.randn(N, K, P, Q, device="cuda").to(BF))
+    base = torch.randn(K, C, R, R, device="cuda").contiguous(memory_format=torch.channels_last)
+    out = base.clone(memory_format=torch.preserve_format)
+    ops.conv_wgrad(dy, x, (K, C, R, R), stride, pad, out=out, splits=splits)
+    ref = REF.conv_wgrad_ref(dy, x, (K, C, R, R), stride, pad).float() + base
+    assert rel_err(out, ref) < 1e-2
 
 
 HALO_CASES = [
@@ -624,7 +716,7 @@ def test_fused_update_virtual_replicas_one_gpu(mode, opt):
     grp = FusedGroup.for_threads([copy.deepcopy(base).cuda() for _ in range(n)], devs, opt, dtype=torch.float32,
                                  comm="native", mode=mode)
     for r in grp.replicas:
-        grp.comm.plans[id(r)][0].set_max_spins(1 << 22)
+        grp.comm.set_max_spins(r, 1 << 22)
     ref, st = copy.deepcopy(base), fd.state(opt, base)
     g_ = torch.Generator().manual_seed(5)
     x = torch.rand(3 * n, 3, 32, 32, generator=g_)
