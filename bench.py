@@ -9,19 +9,35 @@ stream; the value is computed from the MAX over ranks.  Rank 0 prints ONE JSON l
 Config = BASELINE.json #2: ResNet-34, bf16, batch 96/GPU, 224x224x3, Momentum(0.01, 0.9),
 mean softmax-CE, synthetic data, random-init weights (reference recipe README.md:21-52).
 
+Two numbers per run:
+
+``value``  device-timed step loop with device-resident inputs (kernel-only number).
+``e2e``    the same metric through the package's PUBLIC API, the call a user makes, with every step's batch copied
+           host -> device from pinned memory (the native staging ring) and every step's loss read device -> host:
+             1 GPU        task mode   ``prepare_training -> train``            (reference README.md:21-52)
+             N GPUs       process mode ``syncgrads`` server + ``start`` workers (reference bin/driver.jl:22-41),
+                          one worker per torchrun rank, fused transport (gradients never leave the GPUs)
+           (``--api task`` with ``--mode task`` runs the N-GPU task mode in ONE process instead).
+
 Implementations (``--impl``):
   native     this repo's B200 path: hand-written sm_100a kernels + fused all-reduce/update,
              whole step replayed from one CUDA graph            (default)
   torch      this repo's engine with PyTorch/cuDNN layer ops + the fused native update
-  ddp        baseline B2: PyTorch DDP (NCCL all-reduce) + cuDNN + torch SGD
+  ddp        baseline B2: PyTorch DDP (NCCL all-reduce) + cuDNN + torch SGD, eager
+  ddp_tuned  baseline B2, tuned: static inputs, fused optimiser, the whole DDP step captured in a CUDA graph
+  staged     baseline B1: the reference ALGORITHM on cuDNN ops in fp32 — per-tensor star gather to the HOST GPU,
+             N-1 add passes + divide there, star broadcast, per-tensor optimiser on every replica, two barriers per
+             step (src/ddp_tasks.jl:174-247) — one process, a thread per GPU (rank 0 drives all GPUs under torchrun)
   reference  the unmodified reference (Julia; cannot be installed here) -> "unavailable" line
 """
 from __future__ import annotations
 
 import argparse
+import contextlib
 import json
 import os
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +49,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="native", choices=["native", "torch", "ddp", "reference"])
+    ap.add_argument("--impl", default="native", choices=["native", "torch", "ddp", "ddp_tuned", "staged", "reference"])
+    ap.add_argument("--api", default="auto", choices=["auto", "trainer", "task", "process"],
+                    help="public API used for the end-to-end number (auto: task on 1 GPU, process on N)")
     ap.add_argument("--model", default="resnet34", choices=["resnet18", "resnet34", "resnet50", "tiny"])
     ap.add_argument("--batch", type=int, default=96, help="per-GPU batch (README.md:43)")
     ap.add_argument("--opt", default="momentum", choices=["momentum", "adam"])
@@ -54,61 +72,220 @@ def reference_arm():
     print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
-def task_mode(args):
-    """Task-based parallelism (reference README.md:21-52): one process, one thread and one CUDA graph per GPU, the fused
-    kernel exchanging gradients through UVA peer pointers.  Same timing rules as the process mode."""
-    import copy
-    from concurrent.futures import ThreadPoolExecutor
+METRIC = {"resnet34": "ResNet-34 ImageNet-shape training throughput"}
 
+
+def make_model(fd, name, nclasses=1000):
+    ctor = {"resnet18": fd.models.ResNet18, "resnet34": fd.models.ResNet34, "resnet50": fd.models.ResNet50}
+    if name == "tiny":
+        return fd.tiny_convnet(10), 32, 10
+    return ctor[name](nclasses), None, nclasses
+
+
+def make_opt(fd, name):
+    return fd.Momentum(0.01, 0.9) if name == "momentum" else fd.ADAM()
+
+
+class StepTimer:
+    """``on_step`` hook of the public training loops: after step W barrier + synchronize + record, after step W+K
+    record again.  Also issues the per-step device -> host read of the loss (asynchronous copy into pinned memory)."""
+
+    def __init__(self, torch, devs, W, K, barrier):
+        self.torch, self.devs, self.W, self.K, self.barrier = torch, devs, W, K, barrier
+        self.e0 = [torch.cuda.Event(enable_timing=True) for _ in devs]
+        self.e1 = [torch.cuda.Event(enable_timing=True) for _ in devs]
+        self.host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.t0 = self.t1 = None
+        self.done = False
+
+    def _sync(self):
+        for d in self.devs:
+            self.torch.cuda.synchronize(d)
+
+    def __call__(self, j, info):
+        torch = self.torch
+        l = info.get("loss") if isinstance(info, dict) else None
+        if l is not None and torch.is_tensor(l):
+            self.host_loss.copy_(l.detach().reshape(1).float(), non_blocking=True)  # D2H read of this step's result
+        if j == self.W:
+            self._sync()
+            self.barrier()
+            self.t0 = time.perf_counter()
+            for e, d in zip(self.e0, self.devs):
+                e.record(torch.cuda.current_stream(d))
+        elif j == self.W + self.K:
+            for e, d in zip(self.e1, self.devs):
+                e.record(torch.cuda.current_stream(d))
+            self._sync()
+            self.t1 = time.perf_counter()
+            self.barrier()
+            self.done = True
+
+    def ms(self):
+        return max(a.elapsed_time(b) for a, b in zip(self.e0, self.e1))
+
+
+def u8_minibatch(fd, period=4):
+    """``minibatch_fn(shard, n)`` handing out ``period`` pre-generated uint8 NHWC synthetic batches in turn (= the depth of
+    the staging ring, so after the first lap every pinned slot already holds its batch and the per-step host work is the
+    H2D copy alone; the data is synthetic either way)."""
+    from fluxdist.data import synthetic_minibatch
+
+    cache, count = {}, {}
+
+    def fn(shard, n):
+        k = id(shard)
+        if k not in cache:
+            cache[k] = [synthetic_minibatch(shard, n, u8=True) for _ in range(period)]
+            count[k] = 0
+        b = cache[k][count[k] % period]
+        count[k] += 1
+        return b
+
+    return fn
+
+
+class _Cyclic:
+    """Tensor-like view that repeats a bank of ``per`` rows ``n`` rows long without materialising it (the workers slice
+    whole batches out of the cycle's sample set, ``src/sync.jl:136``)."""
+
+    def __init__(self, bank, n):
+        self.bank, self.n = bank, n
+        self.shape = (n,) + tuple(bank.shape[1:])
+        self.dtype = bank.dtype
+
+    def __getitem__(self, sl):
+        per = self.bank.shape[0]
+        lo = sl.start % per
+        return self.bank[lo:lo + (sl.stop - sl.start)]
+
+
+class _U8Worker:
+    """Picklable ``minibatch_fn(tree, key, nsamples)`` of the process-mode workers: uint8 NHWC synthetic batches (four
+    distinct batches cycled: the sample set of a cycle is synthetic anyway, and 1.5 GB of host copies per rank are not
+    what is being measured)."""
+
+    def __init__(self, batch):
+        self.batch = batch
+
+    def __call__(self, tree, key, nsamples):
+        from fluxdist.data import synthetic_minibatch
+
+        per = min(nsamples, self.batch * 4)
+        x, y = synthetic_minibatch(key, per, u8=True)
+        return _Cyclic(x, nsamples), _Cyclic(y, nsamples)
+
+
+# ------------------------------------------------------------------------------------------ public-API end-to-end runs
+def e2e_task(args, fd, torch, devs, W, K, barrier, hw, nclasses, engine="fused", dtype=None, input_="u8"):
+    """Task-based public API: prepare_training -> train (README.md:21-52), pinned staging ring, on-GPU normalisation."""
+    from fluxdist.data import SyntheticKey
+
+    model, _, _ = make_model(fd, args.model, nclasses)
+    opt = make_opt(fd, args.opt)
+    n = len(devs)
+    key = SyntheticKey(100000 * n, nclasses=nclasses, shape=(3, hw, hw))
+    steps = W + K
+    setup, buffer = fd.prepare_training(model, key, devs, opt, args.batch, cycle=steps, buffersize=4, engine=engine,
+                                        onehot=False, loss=fd.logitcrossentropy, dtype=dtype, input=input_,
+                                        minibatch_fn=(u8_minibatch(fd) if input_ == "u8" else None))
+    tdevs = [d.torch_device for d in devs]
+    timer = StepTimer(torch, tdevs, W, K, barrier)
+    with contextlib.redirect_stdout(sys.stderr):  # the loop prints "Num Missed"; stdout carries the JSON line only
+        fd.train(fd.logitcrossentropy, setup, buffer, opt, on_step=timer, log_every=10 ** 9, eval_every=10 ** 9)
+    assert timer.done, "training loop ended before the timed region completed"
+    h2d = args.batch * hw * hw * 3 + args.batch * 8 if input_ == "u8" else args.batch * hw * hw * 3 * 4 + args.batch * 8
+    info = {"api": "prepare_training->train (task mode)", "loader": type(setup.dls[0]).__name__,
+            "wall_ms_per_step": (timer.t1 - timer.t0) * 1e3 / K}
+    if setup.engine is not None:
+        info["comm"] = getattr(setup.engine.replicas[0], "comm_info", {})
+        setup.engine.close()
+    return timer.ms(), h2d, 4, info
+
+
+def e2e_process(args, fd, torch, dist, rank, world, dev, W, K, barrier, hw, nclasses):
+    """Process-based public API: syncgrads server (rank 0) + start(workers=[rank]) on every torchrun rank, channels over
+    the job's c10d store, fused transport (bin/driver.jl:22-41; src/sync.jl:36-170,214-232)."""
+    from fluxdist.data import SyntheticKey
+    from fluxdist.parallel.channels import StoreChannel
+    from fluxdist.parallel.process import start, syncgrads
+
+    model, _, _ = make_model(fd, args.model, nclasses)
+    opt = make_opt(fd, args.opt)
+    store = dist.distributed_c10d._get_default_store()
+    rcs = [StoreChannel(store, f"fdbench/in/{w}", poll_s=0.002) for w in range(world)]
+    ops_ = [StoreChannel(store, f"fdbench/out/{w}", poll_s=0.002) for w in range(world)]
+    server = None
+    if rank == 0:
+        server = threading.Thread(target=syncgrads, args=(rcs, ops_), daemon=True, name="fluxdist-syncgrads")
+        server.start()
+    steps = W + K
+    key = SyntheticKey(100000, nclasses=nclasses, shape=(3, hw, hw))
+    timer = StepTimer(torch, [dev], W, K, barrier)
+    with contextlib.redirect_stdout(sys.stderr):
+        futs = start(fd.logitcrossentropy, None, key, model, [rank], rcs, ops_, opt=opt, world=world, spawn=False,
+                     transport="fused", devices=[fd.CudaDevice(dev.index, dev.index)], nsamples=args.batch * steps,
+                     batchsize=args.batch, cycles=1, minibatch_fn=_U8Worker(args.batch), eval_every=0, on_step=timer)
+        futs[0].result()
+    if server is not None:
+        server.join(timeout=60)
+    assert timer.done, "worker ended before the timed region completed"
+    h2d = args.batch * hw * hw * 3 + args.batch * 8
+    return timer.ms(), h2d, 4, {"api": "syncgrads + start(workers=[rank], transport='fused') (process mode)",
+                                "wall_ms_per_step": (timer.t1 - timer.t0) * 1e3 / K}
+
+
+# ------------------------------------------------------------------------------------------ B1: staged (reference algorithm)
+def staged_main(args):
+    """Baseline B1.  One process, a thread per GPU, engine="staged": fp32, cuDNN ops, markbuffer gather to HOST,
+    sync_buffer mean, getbuffer broadcast, per-tensor optimiser — the reference's own step structure."""
     import torch
+    import torch.distributed as dist
 
     import fluxdist as fd
-    from fluxdist.parallel import FusedGroup
-    from fluxdist.parallel.engine import graphed_replica_step
+    from fluxdist.utils.tracing import ClockSampler
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
     n = args.gpus
-    fd.nn.set_backend("native")
-    torch.manual_seed(0)
-    ctor = {"resnet18": fd.models.ResNet18, "resnet34": fd.models.ResNet34, "resnet50": fd.models.ResNet50}
-    base = ctor.get(args.model, fd.models.ResNet34)(1000).to(memory_format=torch.channels_last)
-    devs = fd.cuda_devices(n)
-    opt = fd.Momentum(0.01, 0.9) if args.opt == "momentum" else fd.ADAM()
-    models = [copy.deepcopy(base).to(d.torch_device) for d in devs]
-    grp = FusedGroup.for_threads(models, devs, opt, loss=fd.logitcrossentropy, comm="native")
-    B, K, W, hw = args.batch, args.steps, max(args.warmup, 3), args.hw
-    xs = [torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, device=d.torch_device) for d in devs]
-    ys = [torch.randint(0, 1000, (B,), device=d.torch_device) for d in devs]
-    pool = ThreadPoolExecutor(n)
+    rec = None
+    if rank == 0:
+        fd.nn.set_backend("torch")
+        torch.backends.cudnn.benchmark = True
+        devs = fd.cuda_devices(n)
+        _, hw_, nclasses = make_model(fd, args.model)
+        hw = hw_ or args.hw
+        W, K = max(args.warmup, 3), args.steps
+        sampler = ClockSampler(0, 10).start(paused=True)
 
-    def one(i):
-        return graphed_replica_step(grp.replicas[i], xs[i], ys[i], fd.logitcrossentropy)
+        def barrier():
+            sampler.resume()
 
-    def step_all():
-        return [f.result() for f in [pool.submit(one, i) for i in range(n)]]
-
-    for _ in range(W):
-        step_all()
-    for d in devs:
-        torch.cuda.synchronize(d.torch_device)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in devs]
-    for (a, _), d in zip(ev, devs):
-        with torch.cuda.device(d.torch_device):
-            a.record(torch.cuda.current_stream(d.torch_device))
-    for _ in range(K):
-        out = step_all()
-    for (_, b), d in zip(ev, devs):
-        with torch.cuda.device(d.torch_device):
-            b.record(torch.cuda.current_stream(d.torch_device))
-    for d in devs:
-        torch.cuda.synchronize(d.torch_device)
-    ms = max(a.elapsed_time(b) for a, b in ev)
-    rec = {"metric": "ResNet-34 ImageNet-shape training throughput", "value": B * n * K / (ms / 1e3), "unit": "images/sec",
-           "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "bf16", "data": "synthetic (device-resident uint8 images)", "impl": "native",
-           "config": {"model": args.model, "global_batch": B * n, "parallelism": f"dp{n}", "mode": "task (1 process, thread per GPU)",
-                      "comm": getattr(grp.replicas[0], "comm_info", {})},
-           "final_loss": float(out[0].item()), "synced": grp.ensure_synced()}
-    print(json.dumps(rec))
+        ms, h2d, d2h, info = e2e_task(args, fd, torch, devs, W, K, barrier, hw, nclasses, engine="staged",
+                                      dtype=torch.float32, input_="float")
+        clocks = sampler.stop()
+        value = args.batch * n * K / (ms / 1e3)
+        rec = {"metric": METRIC.get(args.model, f"{args.model} training throughput"), "value": value, "unit": "images/sec",
+               "n_gpus": n, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "fp32", "data": "synthetic (float32 images), random-init weights",
+               "impl": "staged",
+               "config": {"model": args.model, "global_batch": args.batch * n, "per_gpu_batch": args.batch,
+                          "image": [hw, hw, 3], "optimizer": args.opt, "parallelism": f"dp{n}", "cuda_graph": False,
+                          "algorithm": "reference: star gather to HOST GPU, N-1 adds + divide, star broadcast, per-tensor "
+                                       "optimiser (B1, BASELINE.md §4)", **info},
+               "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
+                          "reasons": clocks.get("reasons", [])},
+               "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "ms_per_step": ms / K}, "gpu_launches": 0}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rec is not None:
+        print(json.dumps(rec))
     return 0
 
 
@@ -117,6 +294,8 @@ def main():
     if args.impl == "reference":
         reference_arm()
         return 0
+    if args.impl == "staged":
+        return staged_main(args)
 
     import torch
     import torch.distributed as dist
@@ -124,14 +303,13 @@ def main():
     import fluxdist as fd
     from fluxdist.utils.tracing import ClockSampler
 
-    if args.mode == "task":
-        return task_mode(args)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device", "impl": args.impl}))
         return 1
+    task_mode = args.mode == "task" and world == 1 and args.gpus > 1
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -139,68 +317,12 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.benchmark = True
 
-    nclasses = 1000
-    ctor = {"resnet18": fd.models.ResNet18, "resnet34": fd.models.ResNet34, "resnet50": fd.models.ResNet50}
     torch.manual_seed(0)
-    if args.model == "tiny":
-        model, hw, nclasses = fd.tiny_convnet(10), 32, 10
-    else:
-        model, hw = ctor[args.model](nclasses), args.hw
-    opt = fd.Momentum(0.01, 0.9) if args.opt == "momentum" else fd.ADAM()
+    model, hw_, nclasses = make_model(fd, args.model)
+    hw = hw_ or args.hw
+    opt = make_opt(fd, args.opt)
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
-
-    # synthetic uint8 images in pinned host memory (what the staging ring carries)
-    g = torch.Generator().manual_seed(1234 + rank)
-    host_x = [torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
-    host_y = [torch.randint(0, nclasses, (B,), dtype=torch.int64, generator=g).pin_memory() for _ in range(2)]
-    host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
-    h2d_bytes = host_x[0].numel() + host_y[0].numel() * 8
-    d2h_bytes = 4
-
-    if args.impl in ("native", "torch"):
-        from fluxdist.parallel.engine import Trainer
-
-        tr = Trainer(model, opt, fd.CudaDevice(local_rank, local_rank), B, image_hw=hw, input="u8",
-                     graph=not args.no_graph, backend=("native" if args.impl == "native" else "torch"),
-                     comm="native")
-        tr.step_fn.x.copy_(host_x[0], non_blocking=True)
-        tr.step_fn.y.copy_(host_y[0], non_blocking=True)
-        tr.capture()  # includes 3 eager warm-up steps
-
-        def run_step():
-            return tr.step()
-
-        x_static, y_static = tr.step_fn.x, tr.step_fn.y
-        comm_info = getattr(tr.rep, "comm_info", {})
-    else:  # ddp baseline
-        from torch.nn.parallel import DistributedDataParallel as DDP
-
-        fd.nn.set_backend("torch")
-        m = model.to(dev).to(memory_format=torch.channels_last)
-        ddp = DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True) if world > 1 else m
-        if args.opt == "momentum":
-            topt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, foreach=True)
-        else:
-            topt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True)
-        x_static = torch.zeros(B, hw, hw, 3, dtype=torch.uint8, device=dev)
-        y_static = torch.zeros(B, dtype=torch.int64, device=dev)
-        x_static.copy_(host_x[0])
-        y_static.copy_(host_y[0])
-        mean = torch.tensor(fd.data.MEAN, device=dev).view(1, 3, 1, 1)
-        std = torch.tensor(fd.data.STD, device=dev).view(1, 3, 1, 1)
-        out_loss = torch.zeros((), device=dev)
-
-        def run_step():
-            x = ((x_static.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous(memory_format=torch.channels_last)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
-                l = torch.nn.functional.cross_entropy(ddp(x), y_static)
-            topt.zero_grad(set_to_none=True)
-            l.backward()
-            topt.step()
-            out_loss.copy_(l.detach())
-            return out_loss
-
-        comm_info = {"mode": "nccl-ddp"}
+    ngpu = args.gpus if task_mode else world
 
     def barrier():
         if world > 1:
@@ -214,94 +336,268 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # NVML set-up happens HERE, before any barrier: round 1 started it between the barrier and rank 0's first event,
+    # which made rank 0 enter the timed region late while its peers already spun in the kernel's cross-GPU barrier
+    sampler = ClockSampler(local_rank, 10).start(paused=True) if rank == 0 else None
+
+    # synthetic uint8 images in pinned host memory
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_x = torch.randint(0, 256, (B, hw, hw, 3), dtype=torch.uint8, generator=g).pin_memory()
+    host_y = torch.randint(0, nclasses, (B,), dtype=torch.int64, generator=g).pin_memory()
+
+    launches = 0
+    nanflag = timeout = False
+    comm_info = {}
+    cuda_graph = False
+    if task_mode:
+        # ---------------- task mode in one process: a thread, a replica and a CUDA graph per GPU (UVA peer pointers)
+        import copy
+        from concurrent.futures import ThreadPoolExecutor
+
+        from fluxdist.parallel import FusedGroup
+        from fluxdist.parallel.engine import graphed_replica_step
+
+        fd.nn.set_backend("native" if args.impl == "native" else "torch")
+        devs = fd.cuda_devices(ngpu)
+        base = model.to(memory_format=torch.channels_last)
+        models = [copy.deepcopy(base).to(d.torch_device) for d in devs]
+        grp = FusedGroup.for_threads(models, devs, opt, loss=fd.logitcrossentropy, comm="native")
+        xs = [host_x.to(d.torch_device) for d in devs]
+        ys = [host_y.to(d.torch_device) for d in devs]
+        pool = ThreadPoolExecutor(ngpu)
+
+        def run_step():
+            futs = [pool.submit(graphed_replica_step, grp.replicas[i], xs[i], ys[i], fd.logitcrossentropy)
+                    for i in range(ngpu)]
+            return [f.result() for f in futs][0]
+
+        tdevs = [d.torch_device for d in devs]
+        comm_info = getattr(grp.replicas[0], "comm_info", {})
+        cuda_graph = True
+    elif args.impl in ("native", "torch"):
+        from fluxdist.parallel.engine import Trainer
+
+        tr = Trainer(model, opt, fd.CudaDevice(local_rank, local_rank), B, image_hw=hw, input="u8",
+                     graph=not args.no_graph, backend=("native" if args.impl == "native" else "torch"),
+                     comm="native")
+        tr.step_fn.x.copy_(host_x, non_blocking=True)
+        tr.step_fn.y.copy_(host_y, non_blocking=True)
+        tr.capture()  # eager warm-up steps (state restored afterwards), then one capture
+
+        def run_step():
+            return tr.step()
+
+        tdevs = [dev]
+        comm_info = getattr(tr.rep, "comm_info", {})
+        cuda_graph = not args.no_graph
+    else:  # ddp baselines
+        from torch.nn.parallel import DistributedDataParallel as DDP
+
+        fd.nn.set_backend("torch")
+        m = model.to(dev).to(memory_format=torch.channels_last)
+        tuned = args.impl == "ddp_tuned"
+        ddp = DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True, static_graph=tuned) if world > 1 else m
+        if args.opt == "momentum":
+            topt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, foreach=not tuned, fused=tuned or None)
+        else:
+            topt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=tuned)
+        x_static = torch.zeros(B, hw, hw, 3, dtype=torch.uint8, device=dev)
+        y_static = torch.zeros(B, dtype=torch.int64, device=dev)
+        x_static.copy_(host_x)
+        y_static.copy_(host_y)
+        mean = torch.tensor(fd.data.MEAN, device=dev).view(1, 3, 1, 1)
+        std = torch.tensor(fd.data.STD, device=dev).view(1, 3, 1, 1)
+        out_loss = torch.zeros((), device=dev)
+
+        def body():
+            x = ((x_static.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous(memory_format=torch.channels_last)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                l = torch.nn.functional.cross_entropy(ddp(x), y_static)
+            topt.zero_grad(set_to_none=not tuned)
+            l.backward()
+            topt.step()
+            out_loss.copy_(l.detach())
+
+        graph = None
+        if tuned:
+            # whole DDP step (forward, backward with NCCL bucket all-reduces, fused optimiser) in one CUDA graph
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    for _ in range(11):  # DDP needs >= 11 warm-up iterations on the capture stream before capture
+                        body()
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    body()
+                cuda_graph = True
+            except Exception as e:  # noqa: BLE001 - report the eager number, flagged
+                graph = None
+                comm_info = {"graph_capture_failed": str(e)[:200]}
+
+        def run_step():
+            if graph is not None:
+                graph.replay()
+            else:
+                body()
+            return out_loss
+
+        tdevs = [dev]
+        comm_info = dict(comm_info, mode="nccl-ddp", tuned=tuned)
+
+    def sync_all():
+        for d in tdevs:
+            torch.cuda.synchronize(d)
+
     # ---------------- kernel-only (device-resident input) timing
     for _ in range(W):
         run_step()
+    sync_all()
     barrier()
-    sampler = ClockSampler(local_rank, 10).start() if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
+    if sampler is not None:
+        sampler.resume()  # sets a flag: nothing between the barrier and the first event record
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in tdevs]
+    for (a, _), d in zip(ev, tdevs):
+        a.record(torch.cuda.current_stream(d))
     for _ in range(K):
         out = run_step()
-    e1.record()
+    for (_, b), d in zip(ev, tdevs):
+        b.record(torch.cuda.current_stream(d))
+    sync_all()
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = max_over_ranks(max(a.elapsed_time(b) for a, b in ev))
     clocks = sampler.stop() if sampler is not None else {}
     final_loss = float(out.item())
-
-    # ---------------- end-to-end: pinned H2D of every step's inputs + D2H read of every step's loss
-    e2e = None
-    if not args.no_e2e:
-        copy_stream = torch.cuda.Stream(device=dev)
-        copied = [torch.cuda.Event(), torch.cuda.Event()]
-        consumed = [torch.cuda.Event(), torch.cuda.Event()]
-        dx = [torch.empty_like(x_static) for _ in range(2)]
-        dy = [torch.empty_like(y_static) for _ in range(2)]
-
-        def e2e_loop(n):
-            cur = torch.cuda.current_stream()
-            loss_val = 0.0
-            for i in range(n):
-                s = i & 1
-                with torch.cuda.stream(copy_stream):  # side stream: H2D of step i overlaps compute of step i-1
-                    copy_stream.wait_event(consumed[s])
-                    dx[s].copy_(host_x[s], non_blocking=True)
-                    dy[s].copy_(host_y[s], non_blocking=True)
-                    copied[s].record(copy_stream)
-                cur.wait_event(copied[s])
-                x_static.copy_(dx[s], non_blocking=True)
-                y_static.copy_(dy[s], non_blocking=True)
-                consumed[s].record(cur)
-                o = run_step()
-                host_loss.copy_(o.reshape(1), non_blocking=True)  # D2H read of this step's result
-                if i > 0 and (i % 1 == 0):
-                    pass
-            cur.synchronize()
-            loss_val = float(host_loss.item())
-            return loss_val
-
-        e2e_loop(3)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
-        f0.record()
-        e2e_loop(K)
-        f1.record()
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max_over_ranks(max(f0.elapsed_time(f1), 0.0))
-        e2e = {"value": B * world * K / (ms_e2e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d_bytes,
-               "d2h_bytes_per_step": d2h_bytes, "ms_per_step": ms_e2e / K, "wall_ms_per_step": wall_ms / K}
-
-    launches = 0
-    if args.impl in ("native", "torch"):
+    if task_mode:
+        launches = sum(getattr(gs, "launches_per_step", 0) for r in grp.replicas
+                       for gs in getattr(r, "_graphs", {}).values()) * K
+        stt = grp.check_status(raise_on_timeout=False)
+        nanflag, timeout = stt["nonfinite"], stt["barrier_timeout"]
+        synced = grp.ensure_synced()
+        grp.close()
+    elif args.impl in ("native", "torch"):
         launches = tr.launches_per_step * K
         nanflag, timeout = tr.status()
+        synced = tr.group.ensure_synced()
+        tr.group.close()
+        del tr
     else:
-        nanflag = timeout = False
+        synced = None
+    torch.cuda.empty_cache()
+
+    # ---------------- end-to-end through the public API: pinned H2D of every step's inputs + D2H read of every step's loss
+    e2e = None
+    if not args.no_e2e and args.impl in ("native", "torch"):
+        api = args.api
+        if api == "auto":
+            api = "task" if (world == 1) else "process"
+        fd.nn.set_backend("native" if args.impl == "native" else "torch")
+        try:
+            if api == "task" and world == 1:
+                devs = fd.cuda_devices(ngpu)
+                ms_e, h2d, d2h, info = e2e_task(args, fd, torch, devs, W, K, barrier, hw, nclasses)
+            elif api == "process" and world > 1:
+                ms_e, h2d, d2h, info = e2e_process(args, fd, torch, dist, rank, world, dev, W, K, barrier, hw, nclasses)
+            else:
+                ms_e, h2d, d2h, info = e2e_trainer(args, fd, torch, dev, W, K, barrier, hw, nclasses, local_rank)
+            ms_e = max_over_ranks(ms_e)
+            e2e = {"value": B * ngpu * K / (ms_e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K, **info}
+        except Exception as e:  # noqa: BLE001 - the kernel-only number is still valid; say why e2e is missing
+            import traceback
+
+            e2e = {"error": f"{type(e).__name__}: {str(e)[:300]}", "trace": traceback.format_exc()[-600:]}
+    elif not args.no_e2e:
+        ms_e, h2d, d2h, info = e2e_ddp(torch, run_step, host_x, host_y, x_static, y_static, W, K, barrier)
+        ms_e = max_over_ranks(ms_e)
+        e2e = {"value": B * ngpu * K / (ms_e / 1e3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e / K, **info}
 
     if rank == 0:
-        value = B * world * K / (ms / 1e3)
+        value = B * ngpu * K / (ms / 1e3)
         rec = {
-            "metric": "ResNet-34 ImageNet-shape training throughput" if args.model == "resnet34" else f"{args.model} training throughput",
-            "value": value, "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": W,
+            "metric": METRIC.get(args.model, f"{args.model} training throughput"),
+            "value": value, "unit": "images/sec", "n_gpus": ngpu, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic (uint8 images, random labels), random-init weights",
             "impl": args.impl,
-            "config": {"model": args.model, "global_batch": B * world, "per_gpu_batch": B, "image": [hw, hw, 3],
-                       "optimizer": args.opt, "parallelism": f"dp{world}", "cuda_graph": not args.no_graph,
+            "config": {"model": args.model, "global_batch": B * ngpu, "per_gpu_batch": B, "image": [hw, hw, 3],
+                       "optimizer": args.opt, "parallelism": f"dp{ngpu}", "cuda_graph": bool(cuda_graph),
+                       "mode": "task (1 process, thread per GPU)" if task_mode else "process (1 rank per GPU)",
                        "comm": comm_info,
                        "l2": "per-step working set (activations > 1 GB) far exceeds the 126 MB L2; no explicit flush"},
             "clocks": {"sm_mhz": clocks.get("sm_mhz"), "sm_max_mhz": clocks.get("sm_max_mhz"),
                        "reasons": clocks.get("reasons", [])},
             "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
-            "nonfinite_grad": bool(nanflag), "barrier_timeout": bool(timeout),
+            "nonfinite_grad": bool(nanflag), "barrier_timeout": bool(timeout), "replicas_synced": synced,
         }
         print(json.dumps(rec))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def e2e_trainer(args, fd, torch, dev, W, K, barrier, hw, nclasses, local_rank):
+    """End-to-end with the ``Trainer`` class fed by the native pinned ring (``--api trainer``)."""
+    from fluxdist.data import StagedLoader
+    from fluxdist.parallel.engine import Trainer
+
+    model, _, _ = make_model(fd, args.model, nclasses)
+    tr = Trainer(model, make_opt(fd, args.opt), fd.CudaDevice(local_rank, local_rank), args.batch, image_hw=hw,
+                 input="u8", graph=not args.no_graph, backend=("native" if args.impl == "native" else "torch"),
+                 comm="native")
+    bank_x = torch.randint(0, 256, (args.batch, hw, hw, 3), dtype=torch.uint8)
+    bank_y = torch.randint(0, nclasses, (args.batch,), dtype=torch.int64)
+    dl = StagedLoader.from_batches(lambda i: (bank_x, bank_y), list(range(W + K)), dev, depth=4)
+    tr.capture()
+    timer = StepTimer(torch, [dev], W, K, barrier)
+    for j, (x, y) in enumerate(dl, start=1):
+        l = tr.step(x, y)
+        timer(j, {"loss": l})
+    tr.group.close()
+    return timer.ms(), args.batch * hw * hw * 3 + args.batch * 8, 4, {"api": "Trainer + StagedLoader",
+                                                                      "wall_ms_per_step": (timer.t1 - timer.t0) * 1e3 / K}
+
+
+def e2e_ddp(torch, run_step, host_x, host_y, x_static, y_static, W, K, barrier):
+    """End-to-end of the DDP baselines: double-buffered pinned H2D on a side stream + per-step D2H of the loss."""
+    copy_stream = torch.cuda.Stream()
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    dx = [torch.empty_like(x_static) for _ in range(2)]
+    dy = [torch.empty_like(y_static) for _ in range(2)]
+    host_loss = torch.zeros(1, dtype=torch.float32).pin_memory()
+    cur = torch.cuda.current_stream()
+
+    def loop(n):
+        for i in range(n):
+            s = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[s])
+                dx[s].copy_(host_x, non_blocking=True)
+                dy[s].copy_(host_y, non_blocking=True)
+                copied[s].record(copy_stream)
+            cur.wait_event(copied[s])
+            x_static.copy_(dx[s], non_blocking=True)
+            y_static.copy_(dy[s], non_blocking=True)
+            consumed[s].record(cur)
+            o = run_step()
+            host_loss.copy_(o.reshape(1), non_blocking=True)
+        cur.synchronize()
+
+    loop(W)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    f0.record()
+    loop(K)
+    f1.record()
+    barrier()
+    wall = (time.perf_counter() - t0) * 1e3
+    return f0.elapsed_time(f1), host_x.numel() + host_y.numel() * 8, 4, {"api": "torch DDP loop", "wall_ms_per_step": wall / K}
 
 
 if __name__ == "__main__":

@@ -12,7 +12,8 @@ For bucket sizes 64 KB .. 1 GB (fp32 gradient bytes) compares, at N GPUs of one 
 Device-timed with CUDA events, max over ranks, 5 warm-up + 20 timed launches per point.
 Bytes that must cross NVLink per rank for a two-shot all-reduce of G gradient bytes followed by a
 broadcast of the updated bf16 weights:  in: G*(N-1)/N, out: (G/2)*(N-1)/N  (fp32 grads in, bf16 weights out).
-Roofline time = max(in, out) / 770 GB/s (measured peer-copy bandwidth per direction, B200_PROFILING.md);
+Roofline time = max(in, out) / 770 GB/s (measured peer-copy bandwidth per direction, B200_PROFILING.md); the
+fraction against the nominal 900 GB/s per direction (BASELINE.json) is reported next to it (``frac_of_900``);
 ``bus_gbs`` follows the NCCL convention 2*(N-1)/N * G / t so it is comparable with nccl-tests.
 Prints one JSON line per (variant, size) and a final summary line.
 """
@@ -130,7 +131,8 @@ def main():
             roof = link_bytes / LINK if world > 1 else G * 4.5 / 6.5e12
             rec = {"variant": name, "bytes": G, "n_gpus": world, "us": t * 1e6,
                    "bus_gbs": (2 * (world - 1) / world * G / t / 1e9) if world > 1 else None,
-                   "algo_gbs": G / t / 1e9, "roofline_us": roof * 1e6, "frac_of_roofline": roof / t}
+                   "algo_gbs": G / t / 1e9, "roofline_us": roof * 1e6, "frac_of_roofline": roof / t,
+                   "frac_of_900": (link_bytes / 900e9 / t) if world > 1 else None}
             rows.append(rec)
             if rank == 0:
                 print(json.dumps(rec), flush=True)

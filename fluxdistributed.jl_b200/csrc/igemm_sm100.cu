@@ -861,7 +861,11 @@ int fd_conv_dgrad(const void* dy, const void* w, void* dx, const void* add, cons
     return -1;
   }
   const int P_ = H + 2 * pad - R + 1, Q_ = W + 2 * pad - S + 1;
-  const TileShape ts = pick_shape(((long)N * H * W + BM - 1) / BM, C, bz != nullptr);
+  // the dz epilogue is long (mask + two column reductions + up to three extra tensor reads per element) and only hides
+  // behind the MMAs of the NEXT tile: it keeps the 128 x BN tiles, which give a CTA 2-4 tiles (scripts/dz_bench.py,
+  // 28x28x128: 36.0 us narrow vs 39.5 wide; with the chained mask + addend 49.2 vs 55.1; 14x14 and 7x7: equal or better)
+  TileShape ts = pick_shape(((long)N * H * W + BM - 1) / BM, C, bz != nullptr);
+  if (bz != nullptr && g_force_bn == 0) ts = {(C % 128 == 0) ? 128 : 64, 1};
   const int bn = ts.bn;
   CUtensorMap ma, mb;
   // CUTLASS dgrad corners: lower = pad-(S-1), upper = pad-(S-1) + (W - Q)

@@ -192,14 +192,24 @@ class StagedLoader:
         it = iter(args[1:])
         state = {"first": (x0, y0)}
 
+        held = {}  # pinned slot -> signature of the source tensors it currently holds
+
+        def sig(t):
+            return (t.data_ptr(), tuple(t.shape), t.dtype, t._version)
+
         def produce(sx, sy):
             if state["first"] is not None:
                 x, y = state["first"]
                 state["first"] = None
             else:
                 x, y = batch_fn(next(it))
-            sx.copy_(x)
-            sy.copy_(y)
+            # a source that keeps handing out the same (unmodified) host tensors — cached / synthetic batches cycled with
+            # the period of the ring — is not copied into a slot that already holds it; the H2D copy still happens
+            k = (sig(x), sig(y))
+            if held.get(sx.data_ptr()) != k:
+                sx.copy_(x)
+                sy.copy_(y)
+                held[sx.data_ptr()] = k
 
         return cls(produce, len(args), device, tuple(x0.shape), tuple(y0.shape), x0.dtype, y0.dtype, depth=depth,
                    transform=transform, prefetch=prefetch)

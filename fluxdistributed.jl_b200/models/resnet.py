@@ -69,6 +69,31 @@ class Bottleneck(nn.Module):
             self.downsample = ConvBN(cin, cout, 1, stride, padding=0, relu=False)
 
     def forward(self, x):
+        native = x.is_cuda and x.dtype == torch.bfloat16 and torch.is_grad_enabled() and self.conv1.cin % 64 == 0 \
+            and self.conv1.cout % 64 == 0
+        if native:
+            # the same cross-layer links as BasicBlock (ops/native.py::_ConvBNAct): `mid1` / `mid2` let the dgrad of the
+            # consumer conv apply the producer BN layer's ReLU mask and reduce its backward sums (dz epilogue: conv3's
+            # 1x1 dgrad finishes conv2's BN, conv2's 3x3 dgrad — when stride 1 — finishes conv1's BN)
+            mid1, mid2 = {}, {}
+            if self.downsample is None and self.conv2.stride == 1:
+                # identity skip: conv3 parks the residual gradient, conv1's dgrad epilogue sums it into dx; with the
+                # chain enabled conv1 also finishes the previous block's last BN layer and conv3 offers its own
+                from ..ops import native as _nv
+
+                link = {}
+                if _nv.DZ_CHAIN and getattr(self, "_chain_ok", False):
+                    tail = {"tail": True}
+                    h = self.conv1(x, add_link=link, own_link=mid1, src_link=getattr(x, "_fd_tail", None))
+                    out = self.conv3(self.conv2(h, src_link=mid1, own_link=mid2), residual=x, res_link=link,
+                                     src_link=mid2, own_link=tail)
+                    out._fd_tail = tail
+                    return out
+                h = self.conv1(x, add_link=link, own_link=mid1)
+                return self.conv3(self.conv2(h, src_link=mid1, own_link=mid2), residual=x, res_link=link, src_link=mid2)
+            # projection block: the block input feeds conv1 and the projection, autograd sums their data gradients
+            h = self.conv2(self.conv1(x, own_link=mid1), src_link=mid1, own_link=mid2)
+            return self.conv3(h, residual=self.downsample(x) if self.downsample is not None else x, src_link=mid2)
         idn = x if self.downsample is None else self.downsample(x)
         return self.conv3(self.conv2(self.conv1(x)), residual=idn)
 

@@ -40,6 +40,7 @@ class GraphedStep:
         self.use_graph = graph and rep.dev.is_cuda
         self.warmup = warmup
         self.capture_error_mode = capture_error_mode  # "thread_local" when several replica threads capture at once
+        self.restore_after_warmup = True
         self.launches_per_step = 0
         self._captured = False
 
@@ -50,7 +51,11 @@ class GraphedStep:
         self.out.copy_(l.float())
 
     def capture(self):
-        """Eager warm-up steps (they are real training steps), then capture."""
+        """Eager warm-up steps, then capture.  The warm-up runs real steps on whatever sits in the static buffers (lazy
+        module loading, cuDNN/TMA descriptor caches, allocator pools all have to be warm before a capture), so the
+        replica's weights, optimiser moments, step counters and BN running statistics are snapshotted before and
+        restored after: capturing has no training side effect and the first replay is exactly step 1 (the
+        first batch used to be applied three times).  In multi-replica groups every replica does the same, in step."""
         from .. import ops
 
         rep = self.rep
@@ -58,6 +63,7 @@ class GraphedStep:
             if not self.use_graph:
                 self._captured = True
                 return self
+            snap = rep.snapshot_state() if self.restore_after_warmup else None
             # high priority: the step's critical path (forward, BN backward, dgrad) is issued on this stream; the side
             # stream of the weight-gradient kernels keeps the default (lowest) priority, so when both have CTAs
             # pending the block scheduler places the critical-path ones first
@@ -75,6 +81,9 @@ class GraphedStep:
             with torch.cuda.graph(self.graph, stream=s, capture_error_mode=self.capture_error_mode):
                 self._body()
             self.launches_per_step = (ops.extension().launch_count() - n0) if ops.native_available() else 0
+            if snap is not None:
+                torch.cuda.synchronize(rep.dev.torch_device)
+                rep.restore_state(snap)
             self._captured = True
         return self
 

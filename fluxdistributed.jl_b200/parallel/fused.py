@@ -259,6 +259,32 @@ class FusedReplica:
     def zero_grads(self) -> None:
         self.arena.g32.zero_()
 
+    # ---- snapshot / restore of everything a training step mutates (used to make graph warm-up side-effect free)
+    def snapshot_state(self) -> dict:
+        a = self.arena
+        with device_ctx(self.dev):
+            snap = {"w32": a.w32.clone(), "slots": [s.clone() for s in a.slots],
+                    "w16": a.w16.clone() if a.w16 is not None else None,
+                    "buffers": [b.clone() for b in self.model.buffers()], "step_count": self.step_count}
+            comm = self.group.comm if self.group is not None else None
+            if comm is not None and hasattr(comm, "plans") and id(self) in getattr(comm, "plans", {}):
+                snap["dev_step"] = comm.plans[id(self)][1]["step"].clone()
+        return snap
+
+    def restore_state(self, snap: dict) -> None:
+        a = self.arena
+        with device_ctx(self.dev), torch.no_grad():
+            a.w32.copy_(snap["w32"])
+            for s, t in zip(a.slots, snap["slots"]):
+                s.copy_(t)
+            if a.w16 is not None and snap["w16"] is not None:
+                a.w16.copy_(snap["w16"])
+            for b, t in zip(self.model.buffers(), snap["buffers"]):
+                b.copy_(t)
+            self.step_count = snap["step_count"]
+            if "dev_step" in snap:
+                self.group.comm.plans[id(self)][1]["step"].copy_(snap["dev_step"])
+
     def step(self, x, y, loss: Callable, fused_update: bool = True):
         if self.stream is not None:
             with device_ctx(self.dev), torch.cuda.stream(self.stream):

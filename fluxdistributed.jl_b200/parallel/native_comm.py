@@ -34,11 +34,16 @@ MODE_TWO_SHOT, MODE_ONE_SHOT = 0, 1
 MAX_GRID = 296
 
 
-def _bucket_fracs() -> tuple:
+def _bucket_fracs(world: int = 2) -> tuple:
     """Bucket plan: cumulative size fractions (in backward order) after which a bucket is cut.  The default gives
-    ResNet-34 three buckets: layer4 + fc (62 % of the bytes, ready first), layer3 (31 %), the rest + all 1-D
-    parameters.  ``FLUXDIST_BUCKETS=0`` keeps one bucket launched at the end of the backward pass."""
-    env = os.environ.get("FLUXDIST_BUCKETS", "0.55,0.9")
+    ResNet-34 three buckets on multi-GPU runs: layer4 + fc (62 % of the bytes, ready first), layer3 (31 %), the rest +
+    all 1-D parameters.  A single GPU keeps ONE bucket at the end of the backward pass: there is nothing to exchange,
+    and the update-only kernel runs at 91 % of the copy bandwidth on the whole GPU but competes with the backward pass
+    when launched early on a bounded grid (measured, gpurun_out/r2ab: 19.8k img/s with one bucket, 19.4k with three).
+    ``FLUXDIST_BUCKETS=0`` forces one bucket, ``FLUXDIST_BUCKETS=0.55,0.9`` forces the cuts."""
+    env = os.environ.get("FLUXDIST_BUCKETS")
+    if env is None:
+        return () if world <= 1 else (0.55, 0.9)
     if env.strip() in ("", "0", "off", "none"):
         return ()
     return tuple(float(x) for x in env.split(","))
@@ -110,7 +115,7 @@ class NativeComm:
         shared = max(cu.count(c) for c in set(cu)) > 1  # virtual replicas on one GPU: no early buckets
         for i, (m, d) in enumerate(zip(models, devs)):
             rep = FusedReplica(m, d, opt, n, i, lowp, order="backward",
-                               bucket_fracs=(() if shared else _bucket_fracs()))
+                               bucket_fracs=(() if shared else _bucket_fracs(n)))
             rep._native_comm = comm
             reps.append(rep)
         share = max(cu.count(c) for c in set(cu))
@@ -140,7 +145,7 @@ class NativeComm:
         tdev = dev.torch_device
         mc = (0, 0, 0)
         if world == 1:
-            rep = FusedReplica(model, dev, opt, 1, 0, lowp, order="backward", bucket_fracs=_bucket_fracs())
+            rep = FusedReplica(model, dev, opt, 1, 0, lowp, order="backward", bucket_fracs=_bucket_fracs(1))
             g_ptrs, w32_ptrs = [rep.arena.g32.data_ptr()], [rep.arena.w32.data_ptr()]
             w16_ptrs = [rep.arena.w16.data_ptr() if rep.arena.w16 is not None else 0]
             flags = torch.zeros(comm.FLAG_WORDS, dtype=torch.int32, device=tdev)
@@ -156,7 +161,7 @@ class NativeComm:
                 return t
 
             rep = FusedReplica(model, dev, opt, world, rank, lowp, alloc=alloc, order="backward",
-                               bucket_fracs=_bucket_fracs())
+                               bucket_fracs=_bucket_fracs(world))
             a = rep.arena
             dist.broadcast(a.w32, src=0, group=group)  # replicas start identical
             if a.w16 is not None:

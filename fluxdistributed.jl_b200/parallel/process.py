@@ -91,6 +91,45 @@ def syncgrads(ip: Sequence, op: Sequence, *, verbose: bool = False, device=None,
 
 
 # --------------------------------------------------------------------------- worker (C20)
+class _TokenPump:
+    """Posts per-step tokens to the gradient server (``c.put`` / ``op.take``) from a helper thread.  With the fused
+    transport the bytes move inside the kernel over NVLink and NaN agreement happens there too, so the server only has
+    to *see* the steps (protocol parity with ``src/sync.jl:36-81``); nothing on the training path waits for it."""
+
+    def __init__(self, c, op, lg, p):
+        import queue
+
+        self.c, self.op, self.lg, self.p = c, op, lg, p
+        self.q: "queue.Queue" = queue.Queue()
+        self.err: Optional[BaseException] = None
+        self.served = 0
+        self.t = threading.Thread(target=self._run, daemon=True, name=f"fluxdist-tokens-{p}")
+        self.t.start()
+
+    def _run(self):
+        try:
+            while True:
+                tok = self.q.get()
+                if tok is None:
+                    return
+                self.c.put(tok)
+                self.op.take()
+                self.served += 1
+        except BaseException as e:  # noqa: BLE001
+            self.err = e
+
+    def post(self, tok) -> None:
+        if self.err is not None:
+            raise self.err
+        self.q.put(tok)
+
+    def close(self, timeout: float = 120.0) -> None:
+        self.q.put(None)
+        self.t.join(timeout)
+        if self.err is not None:
+            raise self.err
+
+
 def _maybetuple(y):
     return y if isinstance(y, tuple) else (y,)
 
@@ -98,8 +137,9 @@ def _maybetuple(y):
 def _worker_loop(rank: int, nworkers: int, loss, tree, m: nn.Module, key, c, op, *, device, verbose: bool,
                  nsamples: int, batchsize: int, opt: Rule, class_idx, cycles: int, saveweights: bool,
                  st, val, minibatch_fn, weights_root: str, model_name: str, save_every: int,
-                 transport: str, logger=None):
-    from ..data import DataLoader
+                 transport: str, logger=None, eval_every: int = 10, use_graph: Optional[bool] = None,
+                 on_step: Optional[Callable] = None, status_every: int = 10):
+    from ..data import DataLoader, StagedLoader
 
     lg = logger or get_logger()
     dev = as_device(device)
@@ -112,7 +152,7 @@ def _worker_loop(rank: int, nworkers: int, loss, tree, m: nn.Module, key, c, op,
         gm = copy.deepcopy(m).to(dev.torch_device)
         if val is None:
             lg.info(f"Worker {p} does not have validation set")
-            val_ = minibatch_fn(tree, key, 100) if minibatch_fn else None
+            val_ = minibatch_fn(tree, key, 100) if (minibatch_fn and eval_every) else None
         else:
             val_ = val
         gval = None
@@ -122,36 +162,64 @@ def _worker_loop(rank: int, nworkers: int, loss, tree, m: nn.Module, key, c, op,
                 vl = float(loss(gm(gval[0]), gval[1]))
             lg.info(f"Worker {p} ready to train")
             lg.info(f"Worker {p} starting with loss: {vl}")
+        sts_given = st is not None
         if st is None:
             st = opt_state(opt, gm)
         else:
             st = fmap(lambda t: t.to(dev.torch_device) if isinstance(t, torch.Tensor) else t, st)
 
         engine = None
+        tokens = None
         if transport == "fused":
             from .fused import FusedGroup
 
+            if dev.is_cuda and any(pp.dim() == 4 for pp in gm.parameters()):
+                gm = gm.to(memory_format=torch.channels_last)
             engine = FusedGroup.for_process(gm, dev, opt, loss=loss)
+            rep = engine.replicas[0]
+            if sts_given:
+                # resume: moments and step counter go into the arena (the logical state the reference passes as `sts=`,
+                # src/sync.jl:101,127-129); ADVICE r1: the fused transport used to ignore it
+                rep.load_state_tree(st)
+            graphed = dev.is_cuda and engine.comm.name == "native" if use_graph is None else bool(use_graph)
+            # the channels carry one token per step (step id, NaN flag): posted from a helper thread so the gradient
+            # server stays informed without the training loop ever waiting for a host round trip
+            tokens = _TokenPump(c, op, lg, p)
 
         step = 0
         for n in range(1, cycles + 1):
             if n % 5 == 0:
                 lg.info(f"Cycle: {n}")
             data = minibatch_fn(tree, key, nsamples)
-            dl = DataLoader(lambda b: tuple(t.to(dev.torch_device, non_blocking=True) for t in b), data,
-                            batchsize=batchsize)
+            if engine is not None and dev.is_cuda:
+                # pinned staging ring: fixed pinned slots, H2D on a copy stream, event hand-off
+                nb = data[0].shape[0] // batchsize
+                dl = StagedLoader.from_batches(
+                    lambda i, _d=data: tuple(t[i * batchsize:(i + 1) * batchsize] for t in _d), list(range(nb)),
+                    dev.torch_device) if nb > 0 else []
+            else:
+                dl = DataLoader(lambda b: tuple(t.to(dev.torch_device, non_blocking=True) for t in b), data,
+                                batchsize=batchsize)
             for i, d in enumerate(dl, start=1):
                 x, y = d
                 step += 1
                 if engine is not None:
-                    l = engine.replicas[0].step(x, y, loss, fused_update=False)
-                    c.put({"__token__": True, "step": step, "nan": bool(l != l)})
-                    tok = op.take()
-                    if tok.get("nan"):
-                        lg.info(f"Worker {p}: NaN reported at step {step}; skipping update")
-                        engine.replicas[0].zero_grads()
+                    rep = engine.replicas[0]
+                    if graphed:
+                        from .engine import graphed_replica_step
+
+                        l = graphed_replica_step(rep, x, y, loss)  # one CUDA graph replay: fwd + bwd + fused exchange/update
                     else:
-                        engine.replicas[0].reduce_and_update()
+                        l = rep.step(x, y, loss)
+                    nan = False
+                    if step % status_every == 0:
+                        stt = engine.check_status()  # raises on a barrier timeout (a dead peer)
+                        nan = stt["nonfinite"]
+                        if nan:
+                            lg.info(f"Worker {p}: non-finite reduced gradient reported at step {step}")
+                    tokens.post({"__token__": True, "step": step, "nan": bool(nan)})
+                    if on_step is not None:
+                        on_step(step, {"loss": l})
                 else:
                     dm, _ = gradient(lambda mm: loss(mm(x), *_maybetuple(y)), gm)
                     verbose and lg.info(f"Worker {p} got grads")
@@ -161,16 +229,24 @@ def _worker_loop(rank: int, nworkers: int, loss, tree, m: nn.Module, key, c, op,
                     gnew = fmap(lambda t: t.to(dev.torch_device) if isinstance(t, torch.Tensor) else t, gnew)
                     verbose and lg.info(f"Worker {p} got new grads")
                     gm, st = opt(gm, gnew, st)
-                if i % 10 == 0 and gval is not None:
+                    if on_step is not None:
+                        on_step(step, {})
+                if eval_every and i % eval_every == 0 and gval is not None:
+                    if engine is not None:
+                        engine.sync_to_modules()  # fp32 masters are sharded by owner under the two-shot kernel
                     with torch.no_grad():
                         lg.info(f"Worker {p} at {i} with loss: {float(loss(gm(gval[0]), gval[1]))}")
-            if saveweights and n % save_every == 0 and rank == 0:
-                if engine is not None:
+            if saveweights and n % save_every == 0:
+                if engine is not None:  # collective: every worker gathers; rank 0 writes
                     engine.sync_to_modules()
+                    st = engine.state_trees()[dev]
+            if saveweights and n % save_every == 0 and rank == 0:
                 path = cycle_checkpoint_name(weights_root, p, model_name, n)
                 save_checkpoint(path, gm, st, step=step)
                 lg.info(f"Worker {p} saved {path}")
         if engine is not None:
+            tokens.close()
+            engine.check_status()
             engine.sync_to_modules()
             st = engine.state_trees()[dev]
             engine.close()
@@ -236,16 +312,30 @@ def getgrads(loss, data_tree, ms, key, rc: Sequence, opc: Sequence, *, workers: 
              saveweights: bool = False, sts: Optional[Sequence] = None, vals: Optional[Sequence] = None,
              minibatch_fn: Optional[Callable] = None, spawn: bool = True, weights_root: str = "weights",
              model_name: str = "model", save_every: int = 20, transport: str = "channel",
-             master_port: Optional[int] = None) -> List[Future]:
+             master_port: Optional[int] = None, world: Optional[int] = None, eval_every: int = 10,
+             use_graph: Optional[bool] = None, on_step: Optional[Callable] = None) -> List[Future]:
     """Launch one worker per (model, state, val, worker, device, in-chan, out-chan)
     tuple (``sync.jl:90-170``) and return futures resolving to ``(cpu_model, cpu_state)``.
 
     ``spawn=True`` runs each worker in its own OS process (the reference's
     ``remotecall_wait``); ``spawn=False`` runs them as threads of this process
     (useful on fake devices and in tests).
+
+    ``workers`` may name a subset of the ``world`` workers: only those are hosted by this call.  That is how an
+    externally launched job (``torchrun``: one process per GPU already exists) uses the same front door — every rank
+    calls ``start(..., workers=[rank], world=N, spawn=False, transport="fused")`` with channels that reach the server
+    (``StoreChannel``), and the fused transport forms its group from the job's ``torch.distributed`` world.
     """
     nw = len(rc)
     workers = list(workers) if workers is not None else list(range(nw))
+    if world is not None and len(workers) != len(rc):
+        # channels are indexed by worker id; keep only those of the workers hosted here
+        rc = [rc[w] for w in workers]
+        opc = [opc[w] for w in workers]
+        if isinstance(ms, (list, tuple)) and len(ms) != len(workers):
+            ms = [ms[w] for w in workers]
+        nw = len(workers)
+    world = world if world is not None else nw
     if not isinstance(ms, (list, tuple)):
         ms = [ms for _ in workers]  # sync.jl:83-84
     if devices is None:
@@ -264,12 +354,12 @@ def getgrads(loss, data_tree, ms, key, rc: Sequence, opc: Sequence, *, workers: 
         return dict(device=devices[i], verbose=verbose, nsamples=nsamples, batchsize=batchsize, opt=opt,
                     class_idx=class_idx, cycles=cycles, saveweights=saveweights, st=sts[i], val=vals[i],
                     minibatch_fn=mb, weights_root=weights_root, model_name=model_name, save_every=save_every,
-                    transport=transport)
+                    transport=transport, eval_every=eval_every, use_graph=use_graph, on_step=on_step)
 
     if not spawn:
         def run(i):
             try:
-                futures[i].set_result(_worker_loop(workers[i], nw, loss, data_tree, copy.deepcopy(ms[i]), key,
+                futures[i].set_result(_worker_loop(workers[i], world, loss, data_tree, copy.deepcopy(ms[i]), key,
                                                    rc[i], opc[i], **kw(i)))
             except BaseException as e:  # noqa: BLE001
                 try:

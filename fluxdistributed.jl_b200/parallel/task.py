@@ -88,18 +88,18 @@ def _take_rows(key, idx):
     return key[idx]
 
 
-def _default_minibatch(dataset_name: str, classes, onehot: bool):
+def _default_minibatch(dataset_name: str, classes, onehot: bool, u8: bool = False):
     from ..data import SyntheticKey, dataset, minibatch, synthetic_minibatch
 
     def fn(shard, nsamples):
         if isinstance(shard, SyntheticKey):
-            return synthetic_minibatch(shard, nsamples, onehot=onehot)
+            return synthetic_minibatch(shard, nsamples, onehot=onehot, u8=u8)
         if isinstance(shard, (tuple, list)) and isinstance(shard[0], torch.Tensor):
             n = shard[0].shape[0]
             ix = torch.randint(0, n, (nsamples,))
             return tuple(s[ix] for s in shard)
         tree = dataset(dataset_name)
-        return minibatch(tree, shard, nsamples=nsamples, class_idx=classes, onehot=onehot)
+        return minibatch(tree, shard, nsamples=nsamples, class_idx=classes, onehot=onehot, u8=u8)
 
     return fn
 
@@ -111,7 +111,8 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
                      dataset: str = "imagenet_local", minibatch_fn: Optional[Callable] = None,
                      onehot: bool = True, engine: str = "auto", seed: Optional[int] = None,
                      dtype: Optional[torch.dtype] = None, loss: Optional[Callable] = None,
-                     engine_opts: Optional[dict] = None, staging: str = "auto", resume=None):
+                     engine_opts: Optional[dict] = None, staging: str = "auto", resume=None,
+                     input: str = "float"):
     """Shard ``key`` over ``devices``, replicate model + optimiser state, allocate the
     per-device gradient buffers on ``HOST`` and build one prefetching loader per
     device.  Returns ``(setup, buffer)`` like the reference.
@@ -125,6 +126,9 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
     (``csrc/staging.cpp`` behind ``data.StagedLoader``) — fixed pinned slots filled by the loader thread,
     ``cudaMemcpyAsync`` on a copy stream, event hand-off to the compute stream, so the H2D copy of step i+1 overlaps
     the compute of step i; ``"simple"``: produce on the loader thread and ``.to(device)``.
+
+    ``input="u8"``: batches travel as uint8 NHWC images (4x fewer PCIe bytes than the reference's Float32 upload,
+    ``src/imagenet.jl:39``) and are normalised on the GPU by the first kernel of the step (``ops.normalize_u8``).
 
     ``resume``: a checkpoint path or a loaded checkpoint dict (``utils.save_checkpoint``): model weights, optimiser
     state (moments + step, also into the fused arenas), shard permutation and RNG are restored — the reference resumes
@@ -144,10 +148,8 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
     if resume is not None:
         from ..utils.checkpoint import load_checkpoint
 
-        ckpt = load_checkpoint(resume, model) if isinstance(resume, (str, bytes)) or hasattr(resume, "__fspath__") else resume
-        if not isinstance(resume, dict):
-            pass
-        elif "model" in ckpt:
+        ckpt = resume if isinstance(resume, dict) else load_checkpoint(resume)
+        if "model" in ckpt:
             model.load_state_dict(ckpt["model"])
         saved = (ckpt.get("extra") or {}).get("shard_indices")
         if saved is not None and len(saved) == ndev and all(len(a) == len(b) for a, b in zip(saved, ixs)):
@@ -167,7 +169,7 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
             with device_ctx(HOST):
                 buffer[dev] = fmap(lambda t: None if t is None else t.to(HOST.torch_device, copy=True), zmodel)
 
-    mb = minibatch_fn or _default_minibatch(dataset, classes, onehot)
+    mb = minibatch_fn or _default_minibatch(dataset, classes, onehot, u8=(input == "u8"))
     ds_and_ms: List[Tuple[Any, nn.Module]] = []
     sts: Dict[Any, Tree] = {}
     dls = []
@@ -361,8 +363,14 @@ def train(loss: Callable, setup: Setup, buffer: Dict[Any, Tree], opt: Rule, *, v
             else:
                 gs = [pool.submit(train_step, loss, buffer, dev, m, *bs)
                       for (dev, m), bs in zip(ds_and_ms, mbs)]
-                for g in gs:
-                    g.result()  # BARRIER 1 (ddp_tasks.jl:208); re-raises task errors (errormonitor)
+                errs = []
+                for g in gs:  # BARRIER 1 (ddp_tasks.jl:208): wait for EVERY replica before anything touches `buffer`
+                    try:
+                        g.result()
+                    except BaseException as e:  # noqa: BLE001 - re-raised below (errormonitor)
+                        errs.append(e)
+                if errs:
+                    raise errs[0]
                 with nvtx_range("sync_buffer"):
                     final = sync_buffer(buffer)
                 futs = [pool.submit(update, opt, dnm, g, final, sts[dnm[0]]) for dnm, g in zip(ds_and_ms, gs)]

@@ -29,8 +29,17 @@ for hw, C in [(28, 128), (14, 256), (7, 512)]:
     s0, s1 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
     wss = [N.bn_workspace(C, "cuda") for _ in range(NSET)]
     r = {"hw": hw, "C": C}
-    r["dgrad_us"] = timeit(lambda i: (lambda: ops.conv_dgrad(ds[i], w, ys[i].shape, 1, 1)))
-    r["dgrad_dz_us"] = timeit(lambda i: (lambda: ops.conv_dgrad(ds[i], w, ys[i].shape, 1, 1, bn_epi=(ys[i], None, mean, rstd, gamma, beta, s0, s1))))
+    ext = ops.extension()
+    adds = [cl(torch.randn(B, C, hw, hw, device="cuda").to(BF)) for _ in range(NSET)]
+    for bn_, mt_ in [(0, 0), (128, 1), (128, 2), (256, 1)]:
+        if bn_ and C % bn_:
+            continue
+        ext.set_tile_shape(bn_, mt_)
+        tag = "auto" if not bn_ else f"{bn_}x{mt_}"
+        r[f"dgrad_{tag}"] = timeit(lambda i: (lambda: ops.conv_dgrad(ds[i], w, ys[i].shape, 1, 1)))
+        r[f"dgrad_dz_{tag}"] = timeit(lambda i: (lambda: ops.conv_dgrad(ds[i], w, ys[i].shape, 1, 1, bn_epi=(ys[i], None, mean, rstd, gamma, beta, s0, s1))))
+        r[f"dgrad_dz_add_out_{tag}"] = timeit(lambda i: (lambda: ops.conv_dgrad(ds[i], w, ys[i].shape, 1, 1, add=adds[i], bn_epi=(ys[i], adds[(i + 1) % NSET], mean, rstd, gamma, beta, s0, s1))))
+    ext.set_tile_shape(0, 0)
     r["bn_bwd_fused_us"] = timeit(lambda i: (lambda: N.bn_bwd_fused(ds[i], ys[i], None, mean, rstd, gamma, beta, wss[i], True)))
     r["bn_bwd_apply_us"] = timeit(lambda i: (lambda: N.bn_bwd_apply(ds[i], ys[i], mean, rstd, gamma, s0, s1)))
     print(json.dumps(r), flush=True)

@@ -620,31 +620,93 @@ def test_convbn_module_matches_torch_path():
     assert torch.allclose(m.bn.running_mean, m2.bn.running_mean, atol=1e-2)
 
 
+def _fwd_bwd(m, x, y, mode):
+    mm = copy.deepcopy(m)
+    try:
+        if mode == "native":
+            fd.nn.set_backend("native")
+            lg = mm(x.to(BF))
+            l = fd.logitcrossentropy(lg, y)
+        elif mode == "cudnn_bf16":
+            fd.nn.set_backend("torch")
+            with torch.autocast("cuda", dtype=BF):
+                lg = mm(x)
+                l = F.cross_entropy(lg.float(), y)
+        else:
+            fd.nn.set_backend("torch")
+            lg = mm(x)
+            l = F.cross_entropy(lg, y)
+        l.backward()
+        torch.cuda.synchronize()
+    finally:
+        fd.nn.set_backend("auto")
+    return lg.detach().float(), float(l.detach()), {n: p.grad.detach().float() for n, p in mm.named_parameters()}
+
+
+def _assert_no_worse_than_cudnn_bf16(m, x, y, logits_tol):
+    """The honest yardstick for a bf16 pipeline at random initialisation: PyTorch/cuDNN running the SAME network in bf16
+    autocast.  Against the fp32 run both bf16 pipelines deviate by the same amount (gradients of a randomly initialised
+    34-layer ReLU/BN network are chaotic: cuDNN-bf16 vs fp32 differs by ~0.65 relative per parameter at batch 96 224x224,
+    profiles/numerics_r2.json), so the native path is required to (a) agree with cuDNN-bf16 on the logits within
+    ``logits_tol``, and (b) be no further from fp32 than cuDNN-bf16 is, per parameter, up to 15 % + 0.02."""
+    lg_n, l_n, g_n = _fwd_bwd(m, x, y, "native")
+    lg_b, l_b, g_b = _fwd_bwd(m, x, y, "cudnn_bf16")
+    lg_f, l_f, g_f = _fwd_bwd(m, x, y, "fp32")
+    assert abs(l_n - l_f) < max(2e-2, 2 * abs(l_b - l_f))
+    assert rel_err(lg_n, lg_b) < logits_tol
+    assert rel_err(lg_n, lg_f) < 1.15 * rel_err(lg_b, lg_f) + 5e-3
+    worst = []
+    for n in g_f:
+        en, eb = rel_err(g_n[n], g_f[n]), rel_err(g_b[n], g_f[n])
+        if not en < 1.15 * eb + 0.02:
+            worst.append((n, en, eb))
+    assert not worst, f"native further from fp32 than cuDNN-bf16 on {len(worst)} parameters, e.g. {worst[:4]}"
+
+
 def test_resnet18_native_vs_torch():
     torch.manual_seed(0)
     m = cl_model(fd.ResNet18(100)).cuda()
-    m2 = copy.deepcopy(m)
     x = cl(torch.randn(8, 3, 64, 64, device="cuda"))
     y = torch.randint(0, 100, (8,), device="cuda")
-    fd.nn.set_backend("native")
+    _assert_no_worse_than_cudnn_bf16(m, x, y, logits_tol=2e-2)
+
+
+def test_resnet34_benchmark_shape_native_vs_cudnn():
+    """The BENCHMARKED shape: ResNet-34, batch 96, 224x224 — one forward/backward through every kernel the bench runs."""
+    torch.manual_seed(0)
+    m = cl_model(fd.ResNet34(1000)).cuda()
+    x = cl(torch.randn(96, 3, 224, 224, device="cuda"))
+    y = torch.randint(0, 1000, (96,), device="cuda")
+    _assert_no_worse_than_cudnn_bf16(m, x, y, logits_tol=2.5e-2)
+
+
+def test_loss_curve_native_vs_cudnn_path():
+    """50 training steps (ResNet-18, batch 32, 64x64, Momentum, fused update) from the same seed and data: the native
+    kernels and the cuDNN layer ops produce loss curves that stay as close to each other as the cuDNN-bf16 curve stays
+    to its own rerun with a different (fp32) accumulation — both end at the same loss."""
+    from fluxdist.parallel.engine import Trainer
+
+    def curve(backend, dtype=None, steps=50):
+        torch.manual_seed(1)
+        tr = Trainer(fd.ResNet18(100), fd.Momentum(0.01, 0.9), fd.CudaDevice(0, 0), 32, image_hw=64, input="u8",
+                     graph=False, backend=backend, comm="native", dtype=dtype)
+        g = torch.Generator().manual_seed(2)
+        xs = torch.randint(0, 256, (8, 32, 64, 64, 3), dtype=torch.uint8, generator=g).cuda()
+        ys = torch.randint(0, 100, (8, 32), generator=g).cuda()
+        ls = [float(tr.step(xs[i % 8], ys[i % 8])) for i in range(steps)]
+        tr.group.close()
+        return ls
+
     try:
-        out = m(x.to(BF))
-        l1 = fd.logitcrossentropy(out, y)
-        l1.backward()
+        cn, cb, cf = curve("native"), curve("torch"), curve("torch", torch.float32)
     finally:
         fd.nn.set_backend("auto")
-    fd.nn.set_backend("torch")
-    try:
-        ref = m2(x)
-        l2 = F.cross_entropy(ref, y)
-        l2.backward()
-    finally:
-        fd.nn.set_backend("auto")
-    assert abs(l1.item() - l2.item()) < 0.1
-    g1 = m.layer4[1].conv2.conv.weight.grad
-    g2 = m2.layer4[1].conv2.conv.weight.grad
-    assert rel_err(g1, g2) < 0.3  # bf16 activations + batch-8 BN statistics vs fp32 reference
-    assert rel_err(m.head.fc.weight.grad, m2.head.fc.weight.grad) < 0.1
+    d_nb = max(abs(a - b) for a, b in zip(cn, cb))
+    d_bf = max(abs(a - b) for a, b in zip(cb, cf))
+    assert all(v == v for v in cn)
+    assert abs(cn[0] - cb[0]) < 2e-2 * cb[0]                      # identical start
+    assert d_nb < max(2.0 * d_bf, 0.25), (d_nb, d_bf)              # no further apart than bf16 vs fp32 of the SAME ops
+    assert cn[-1] < 0.25 * cn[0] and abs(cn[-1] - cb[-1]) < 0.1   # both converge to the same loss
 
 
 def test_resnet50_native_smoke():
