@@ -27,7 +27,9 @@ constexpr int TH = 16, TW = 8;       // output tile (pixels); TW = 8 = one swizz
 constexpr int PH = TH + 2, PW = TW + 2;
 constexpr int PATCH_BYTES = PH * PW * 128;                       // 23040
 constexpr int PATCH_STRIDE = (PATCH_BYTES + 1023) / 1024 * 1024;  // 23552
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;      // weight-gradient kernels: producer + MMA + 4 epilogue warps
+constexpr int kEpiWarps = 8;       // fprop / dgrad: two epilogue warps per SM sub-partition, BN/2 columns each (round 2)
+constexpr int kThreadsConv = 64 + 32 * kEpiWarps;
 
 struct HParams {
   int N, H, W;          // image batch / output extent (stride 1, same size)
@@ -66,8 +68,32 @@ FD_DEVINL float2 colsum_transpose_reduce(float (&v)[32], int lane) {
   return make_float2(v[0], 0.f);
 }
 
+// Column sums of a 32x32 fp32 block held one row per lane, through a padded 16-row shared-memory tile (the two
+// half-warps take turns; lane l then walks column l): sum and sum of squares for ~120 instructions and no shuffles.
+FD_DEVINL void halo_column_sums(const float (&f)[32], float* buf, int lane, float& sum, float& sumsq) {
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    if ((lane >> 4) == half) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(buf + (lane & 15) * 36 + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float x = buf[r * 36 + lane];
+      a[r & 3] += x;
+      b[r & 3] += x * x;
+    }
+    __syncwarp();
+  }
+  sum += (a[0] + a[1]) + (a[2] + a[3]);
+  sumsq += (b[0] + b[1]) + (b[2] + b[3]);
+}
+
 template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreadsConv, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HParams P,
                  const int resident_bytes, const int a_stages) {
   using C = HCfg<BN, DGRAD, RESIDENT>;
@@ -100,7 +126,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 128);
+      mbar_init(&tempty[i], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -244,13 +270,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       if (acc == 0) accph ^= 1;
     }
   } else {
+    // eight epilogue warps: warp w drains TMEM lane quadrant (w & 3) and the column half ((w - 2) >> 2) of the tile —
+    // two warps per scheduler fill each other's dependency stalls, and each owns half of the per-tile work, so the
+    // statistics epilogue stays shorter than the 36 N=64 MMAs of a tile (round 2: +11 us -> hidden at 56x56x64)
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    constexpr int NQ = BN / 64;  // 32-column chunks per warp
     int acc = 0;
     uint32_t accph = 0;
     const bool stats = (!DGRAD) && P.sum != nullptr;
-    float stat_s[BN / 32], stat_q[BN / 32];
+    __shared__ __align__(16) float colred_all[kEpiWarps * 16 * 36];
+    float* const colred = colred_all + (warp - 2) * 16 * 36;
+    float stat_s[NQ], stat_q[NQ];
 #pragma unroll
-    for (int q = 0; q < BN / 32; ++q) stat_s[q] = stat_q[q] = 0.f;
+    for (int q = 0; q < NQ; ++q) stat_s[q] = stat_q[q] = 0.f;
     for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
       const int n = mt / (P.tiles_h * P.tiles_w);
       const int rem = mt - n * (P.tiles_h * P.tiles_w);
@@ -261,19 +294,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       bf16* orow = reinterpret_cast<bf16*>(P.out) + (((long)n * P.H + h) * P.W + w) * P.Nout + n0;
-      uint32_t va[BN / 32][32];
+      uint32_t va[NQ][32];
       if (!(P.dbg & 8)) {
 #pragma unroll
-        for (int q = 0; q < BN / 32; ++q)
-          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + q * 32, va[q]);
+        for (int q = 0; q < NQ; ++q)
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + (half * NQ + q) * 32, va[q]);
         tmem_ld_wait();
       }
       // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the stores
       tc_fence_before();
       mbar_arrive(&tempty[acc]);
 #pragma unroll
-      for (int q = 0; q < BN / 32; ++q) {
-        const int c0 = q * 32;
+      for (int q = 0; q < NQ; ++q) {
+        const int c0 = (half * NQ + q) * 32;
         uint32_t(&v)[32] = va[q];
         if (P.add != nullptr && valid) {
           const bf16* arow = reinterpret_cast<const bf16*>(P.add) + (((long)n * P.H + h) * P.W + w) * P.Nout + n0 + c0;
@@ -303,22 +336,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(orow + c0 + j * 8) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         }
-        if (stats) {
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = f[j] * f[j];
-          stat_s[q] += colsum_transpose_reduce(f, lane).x;   // lane L accumulates column c0+L over this CTA's tiles
-          stat_q[q] += colsum_transpose_reduce(sq, lane).x;
-        }
+        if (stats) halo_column_sums(f, colred, lane, stat_s[q], stat_q[q]);  // lane L: column c0+L over this CTA's tiles
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1;
     }
     if (stats) {  // one atomic per (warp, channel) for the whole kernel instead of one per tile
 #pragma unroll
-      for (int q = 0; q < BN / 32; ++q) {
-        atomicAdd(P.sum + n0 + q * 32 + lane, stat_s[q]);
-        atomicAdd(P.sumsq + n0 + q * 32 + lane, stat_q[q]);
+      for (int q = 0; q < NQ; ++q) {
+        atomicAdd(P.sum + n0 + (half * NQ + q) * 32 + lane, stat_s[q]);
+        atomicAdd(P.sumsq + n0 + (half * NQ + q) * 32 + lane, stat_q[q]);
       }
     }
   }
@@ -385,11 +412,12 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
   using C = HCfg<BN, DGRAD, RESIDENT>;
   const int resident_bytes = RESIDENT ? p.chunks * (STEM ? 1 : 9) * C::B_TILE : 0;
   const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
-  int a_stages = (int)((227 * 1024 - 1024 - 512 - b_bytes) / PATCH_STRIDE);
+  constexpr int kStatic = kEpiWarps * 16 * 36 * 4 + 64;  // epilogue reduction scratch (static shared memory)
+  int a_stages = (int)((227 * 1024 - 1024 - 512 - kStatic - b_bytes) / PATCH_STRIDE);
   if (a_stages > 6) a_stages = 6;
   if (p.sum == nullptr && p.sumsq != nullptr) a_stages = 2;  // (debug hook, unused)
   const int smem = a_stages * PATCH_STRIDE + b_bytes + 1024 + 512;
-  if (a_stages < 2 || smem > 227 * 1024) {
+  if (a_stages < 2 || smem + kStatic > 227 * 1024) {
     fd_set_error("conv_halo: shared memory budget exceeded", __FILE__, __LINE__);
     return -1;
   }
@@ -398,7 +426,7 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
   if (grid < p.n_tiles) grid = p.n_tiles;
-  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM><<<grid, kThreads, smem, s>>>(a, b, p, resident_bytes, a_stages);
+  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM><<<grid, kThreadsConv, smem, s>>>(a, b, p, resident_bytes, a_stages);
   FD_LAUNCH_OK();
   return 0;
 }
@@ -420,7 +448,7 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, 
   p.dbg = variant >> 9; variant &= 255;  // bit 8 = statistics buffers pre-zeroed (fd_conv3x3_fprop), bits 9+ = ablation
   // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
   const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
-  const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048;
+  const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048 - (kEpiWarps * 16 * 36 * 4 + 64);
   if (variant == 0) {
     if (res64 <= budget) variant = 1;
     else variant = (Cout % 128 == 0) ? 3 : 2;

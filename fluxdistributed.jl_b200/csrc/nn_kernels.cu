@@ -120,6 +120,23 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
   float* sc = smem;
   float* sh = smem + C;
   const float invM = 1.f / (float)M;
+  const int C8 = C / 8;
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  constexpr int U = 4;  // independent 16-byte loads per tensor in flight per thread
+  // The activation loads do not depend on the per-channel coefficients: the first batch is requested BEFORE the
+  // coefficient prologue (dependent global loads, rsqrt, barrier, the `consumed` atomic), whose ~2 us of latency would
+  // otherwise be fully exposed — the grid is a single wave, every CTA pays it exactly once (round 2).
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  V8 yv[U], rv[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long ii = i0 + u * stride;
+    if (ii < total) {
+      yv[u] = ldg8(y + ii * 8);
+      if (res) rv[u] = ldg8(res + ii * 8);
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float mean, var;
     if (training) {
@@ -158,18 +175,15 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
       if (threadIdx.x == 0) *consumed = 0u;
     }
   }
-  const int C8 = C / 8;
-  const long total = M * C8;
-  const long stride = (long)gridDim.x * blockDim.x;
-  constexpr int U = 4;  // independent 16-byte loads per tensor in flight per thread
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
-    V8 yv[U], rv[U];
+  for (long i = i0; i < total; i += U * stride) {
+    if (i != i0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long ii = i + u * stride;
-      if (ii < total) {
-        yv[u] = ldg8(y + ii * 8);
-        if (res) rv[u] = ldg8(res + ii * 8);
+      for (int u = 0; u < U; ++u) {
+        const long ii = i + u * stride;
+        if (ii < total) {
+          yv[u] = ldg8(y + ii * 8);
+          if (res) rv[u] = ldg8(res + ii * 8);
+        }
       }
     }
 #pragma unroll
@@ -612,6 +626,21 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, con
   float* kb = smem + C;
   float* kc = smem + 2 * C;
   const float invM = 1.f / (float)M;
+  constexpr int U = 4;
+  const int C8 = C / 8;
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  // first batch of loads before the coefficient prologue (see bn_apply_kernel)
+  const long i0 = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  V8 a[U], b[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const long ii = i0 + u * stride;
+    if (ii < total) {
+      a[u] = ldg8(dz + ii * 8);
+      b[u] = ldg8(y + ii * 8);
+    }
+  }
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const float g = gamma[c], r_ = rstd[c], m_ = mean[c];
     const float dg = s0[c] * r_, db = s1[c];
@@ -636,18 +665,15 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, con
       if (threadIdx.x == 0) *consumed = 0u;
     }
   }
-  constexpr int U = 4;
-  const int C8 = C / 8;
-  const long total = M * C8;
-  const long stride = (long)gridDim.x * blockDim.x;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
-    V8 a[U], b[U];
+  for (long i = i0; i < total; i += U * stride) {
+    if (i != i0) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long ii = i + u * stride;
-      if (ii < total) {
-        a[u] = ldg8(dz + ii * 8);
-        b[u] = ldg8(y + ii * 8);
+      for (int u = 0; u < U; ++u) {
+        const long ii = i + u * stride;
+        if (ii < total) {
+          a[u] = ldg8(dz + ii * 8);
+          b[u] = ldg8(y + ii * 8);
+        }
       }
     }
 #pragma unroll
