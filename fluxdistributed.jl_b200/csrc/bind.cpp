@@ -106,6 +106,20 @@ void conv_fprop(at::Tensor x, at::Tensor w, at::Tensor y, int stride, int pad, c
         "conv_fprop");
 }
 // bn_epi (optional): [y, out-or-empty, mean, rstd, gamma, beta, s0, s1] of the BN layer whose output gradient is produced
+static bool parse_bn_epi(const c10::optional<std::vector<at::Tensor>>& bn_epi, const at::Tensor& dx, FdBnEpilogue& bz) {
+  if (!bn_epi.has_value()) return false;
+  const auto& v = *bn_epi;
+  TORCH_CHECK(v.size() == 8, "bn_epi: 8 tensors expected");
+  want(v[0], at::kBFloat16, "bn_epi.y");
+  TORCH_CHECK(v[0].numel() == dx.numel(), "bn_epi.y must have the shape of dx");
+  bz.y = v[0].data_ptr();
+  bz.out = v[1].numel() ? v[1].data_ptr() : nullptr;
+  bz.mean = v[2].data_ptr<float>(); bz.rstd = v[3].data_ptr<float>();
+  bz.gamma = v[4].data_ptr<float>(); bz.beta = v[5].data_ptr<float>();
+  bz.s0 = v[6].data_ptr<float>(); bz.s1 = v[7].data_ptr<float>();
+  return true;
+}
+
 void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::optional<at::Tensor> add,
                 c10::optional<std::vector<at::Tensor>> bn_epi) {
   want(dy, at::kBFloat16, "dy");
@@ -113,19 +127,7 @@ void conv_dgrad(at::Tensor dy, at::Tensor w, at::Tensor dx, int pad, c10::option
   want(dx, at::kBFloat16, "dx");
   c10::cuda::CUDAGuard guard(dy.device());
   FdBnEpilogue bz{};
-  const FdBnEpilogue* bzp = nullptr;
-  if (bn_epi.has_value()) {
-    const auto& v = *bn_epi;
-    TORCH_CHECK(v.size() == 8, "bn_epi: 8 tensors expected");
-    want(v[0], at::kBFloat16, "bn_epi.y");
-    TORCH_CHECK(v[0].numel() == dx.numel(), "bn_epi.y must have the shape of dx");
-    bz.y = v[0].data_ptr();
-    bz.out = v[1].numel() ? v[1].data_ptr() : nullptr;
-    bz.mean = v[2].data_ptr<float>(); bz.rstd = v[3].data_ptr<float>();
-    bz.gamma = v[4].data_ptr<float>(); bz.beta = v[5].data_ptr<float>();
-    bz.s0 = v[6].data_ptr<float>(); bz.s1 = v[7].data_ptr<float>();
-    bzp = &bz;
-  }
+  const FdBnEpilogue* bzp = parse_bn_epi(bn_epi, dx, bz) ? &bz : nullptr;
   check(fd_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), bzp, (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
                       (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), pad, cur_stream()),
         "conv_dgrad");
@@ -291,11 +293,14 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     check(fd_conv3x3_fprop(x.data_ptr(), w.data_ptr(), y.data_ptr(), optf(sum), optf(sumsq), (int)x.size(0), (int)x.size(1),
                            (int)x.size(2), (int)x.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_fprop");
   });
-  m.def("conv3x3_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int variant, c10::optional<at::Tensor> add) {
+  m.def("conv3x3_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int variant, c10::optional<at::Tensor> add,
+                            c10::optional<std::vector<at::Tensor>> bn_epi) {
     c10::cuda::CUDAGuard guard(dy.device());
-    check(fd_conv3x3_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
-                           (int)dx.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_dgrad");
-  });
+    FdBnEpilogue bz{};
+    const FdBnEpilogue* bzp = parse_bn_epi(bn_epi, dx, bz) ? &bz : nullptr;
+    check(fd_conv3x3_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), optptr(add), bzp, (int)dx.size(0), (int)dx.size(1),
+                           (int)dx.size(2), (int)dx.size(3), (int)w.size(0), variant, cur_stream()), "conv3x3_dgrad");
+  }, py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("variant"), py::arg("add") = py::none(), py::arg("bn_epi") = py::none());
   m.def("conv3x3_wgrad", [](at::Tensor dy, at::Tensor x, at::Tensor dw, int splits) {
     c10::cuda::CUDAGuard guard(dy.device());
     check(fd_conv3x3_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
@@ -346,6 +351,19 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
                           gamma.data_ptr<float>(), beta.data_ptr<float>(), dgamma.data_ptr<float>(), dbeta.data_ptr<float>(),
                           dy.data_ptr(), dres.has_value() ? dres->data_ptr() : nullptr, ws.data_ptr(), y.numel() / C, C, relu,
                           cur_stream()), "bn_bwd_fused");
+  });
+  m.def("bn_bwd_pool_fused", [](at::Tensor idx, at::Tensor g, at::Tensor y, at::Tensor mean, at::Tensor rstd, at::Tensor gamma,
+                                at::Tensor beta, at::Tensor dgamma, at::Tensor dbeta, at::Tensor dy, at::Tensor ws) {
+    // idx, g: [N,P,Q,C] (arg-max bytes, pooled gradient); y, dy: [N,H,W,C]
+    want(g, at::kBFloat16, "g");
+    want(y, at::kBFloat16, "y");
+    const int C = (int)y.size(3);
+    TORCH_CHECK((size_t)ws.numel() * ws.element_size() >= fd_bn_ws_bytes(C), "bn workspace too small");
+    c10::cuda::CUDAGuard guard(y.device());
+    check(fd_bn_bwd_pool_fused(idx.data_ptr(), g.data_ptr(), y.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(),
+                               gamma.data_ptr<float>(), beta.data_ptr<float>(), dgamma.data_ptr<float>(),
+                               dbeta.data_ptr<float>(), dy.data_ptr(), ws.data_ptr(), (int)y.size(0), (int)y.size(1),
+                               (int)y.size(2), C, cur_stream()), "bn_bwd_pool_fused");
   });
   m.def("bn_stats", &bn_stats);
   m.def("bn_apply", &bn_apply);

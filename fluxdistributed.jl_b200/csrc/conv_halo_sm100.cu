@@ -43,6 +43,13 @@ struct HParams {
   float* sumsq;
   const void* add;  // optional bf16 tensor (same shape as out) added before the store
   int dbg;  // debug/ablation bits: 1 = skip output stores, 2 = skip patch loads, 4 = skip MMAs
+  // dgrad "dz epilogue" (see igemm_sm100.cu KParams::bz_*): the tensor produced is the gradient w.r.t. the OUTPUT of a
+  // BN(+ReLU) layer; the epilogue applies that layer's ReLU mask (from its post-residual activation bz_out, or
+  // recomputed from y) and reduces sum(dz), sum(dz*(y-mean)) per channel — the first pass of that layer's BN backward
+  const void* bz_y;
+  const void* bz_out;
+  const float *bz_mean, *bz_rstd, *bz_gamma, *bz_beta;
+  float *bz_s0, *bz_s1;
 };
 
 template <int BN, bool DGRAD, bool RESIDENT>
@@ -92,10 +99,12 @@ FD_DEVINL void halo_column_sums(const float (&f)[32], float* buf, int lane, floa
   sumsq += (b[0] + b[1]) + (b[2] + b[3]);
 }
 
-template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false>
+template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false, bool BZ = false>
 __global__ void __launch_bounds__(kThreadsConv, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const HParams P,
                  const int resident_bytes, const int a_stages) {
+  static_assert(!BZ || DGRAD, "the dz epilogue belongs to the data-gradient kernel");
+  __shared__ float bnpar[BZ ? 3 * BN : 4];  // mean | gamma*rstd | beta - mean*gamma*rstd of this CTA's channel tile
   using C = HCfg<BN, DGRAD, RESIDENT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -134,14 +143,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     tmem_alloc(tmem_slot, C::TMEM_COLS);
     tmem_relinquish();
   }
+  // each CTA serves one output-channel tile (so a resident filter slice stays valid) and strides over m-tiles
+  const int nt = blockIdx.x % P.n_tiles;
+  const int n0 = nt * BN;
+  if (BZ) {
+    for (int c = threadIdx.x; c < BN; c += blockDim.x) {
+      const float mu = P.bz_mean[n0 + c], g = P.bz_gamma[n0 + c] * P.bz_rstd[n0 + c];
+      bnpar[c] = mu;
+      bnpar[BN + c] = g;
+      bnpar[2 * BN + c] = P.bz_beta[n0 + c] - mu * g;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
 
-  // each CTA serves one output-channel tile (so a resident filter slice stays valid) and strides over m-tiles
-  const int nt = blockIdx.x % P.n_tiles;
-  const int n0 = nt * BN;
   const int m_first = blockIdx.x / P.n_tiles;
   const int m_step = gridDim.x / P.n_tiles;
   // STEM: the 7x7/2 stem as a 4x4/1 conv over the space-to-depth input; the A tile of filter row `a` is a plain
@@ -278,7 +295,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     constexpr int NQ = BN / 64;  // 32-column chunks per warp
     int acc = 0;
     uint32_t accph = 0;
-    const bool stats = (!DGRAD) && P.sum != nullptr;
+    const bool stats = ((!DGRAD) && P.sum != nullptr) || BZ;
     __shared__ __align__(16) float colred_all[kEpiWarps * 16 * 36];
     float* const colred = colred_all + (warp - 2) * 16 * 36;
     float stat_s[NQ], stat_q[NQ];
@@ -323,29 +340,64 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           }
         }
         float f[32];
+        if (BZ) {
+          // dz = mask * dx; accumulate sum dz and sum dz*(y - mean) of this lane's column over the CTA's tiles
+          const long off = (((long)n * P.H + h) * P.W + w) * P.Nout + n0 + c0;
+          float qv[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          const uint32_t pk = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-          const float2 back = unpack_bf16x2(pk);
-          f[j] = valid ? back.x : 0.f;       // statistics are taken over the rounded values bn_apply will read
-          f[j + 1] = valid ? back.y : 0.f;
-          v[j >> 1] = pk;
+          for (int j4 = 0; j4 < 4; ++j4) {
+            uint4 yv = make_uint4(0, 0, 0, 0), ov = yv;
+            if (valid) {
+              yv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_y) + off + j4 * 8);
+              if (P.bz_out) ov = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_out) + off + j4 * 8);
+            }
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 y2 = unpack_bf16x2(yw[e]), o2 = unpack_bf16x2(ow[e]);
+#pragma unroll
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int jj = j4 * 8 + 2 * e + h2;
+                const float yy = h2 ? y2.y : y2.x;
+                const float pre = P.bz_out ? (h2 ? o2.y : o2.x) : (yy * bnpar[BN + c0 + jj] + bnpar[2 * BN + c0 + jj]);
+                const float dz = (valid && pre > 0.f) ? __uint_as_float(v[jj]) : 0.f;
+                f[jj] = dz;
+                qv[jj] = dz * (yy - bnpar[c0 + jj]);
+              }
+            }
+          }
+          float unused = 0.f;
+          halo_column_sums(f, colred, lane, stat_s[q], unused);
+          halo_column_sums(qv, colred, lane, stat_q[q], unused);
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) v[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            const uint32_t pk = pack_bf16x2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+            const float2 back = unpack_bf16x2(pk);
+            f[j] = valid ? back.x : 0.f;       // statistics are taken over the rounded values bn_apply will read
+            f[j + 1] = valid ? back.y : 0.f;
+            v[j >> 1] = pk;
+          }
         }
         if (valid && !(P.dbg & 1)) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(orow + c0 + j * 8) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         }
-        if (stats) halo_column_sums(f, colred, lane, stat_s[q], stat_q[q]);  // lane L: column c0+L over this CTA's tiles
+        if (stats && !BZ) halo_column_sums(f, colred, lane, stat_s[q], stat_q[q]);  // lane L: column c0+L over this CTA's tiles
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1;
     }
     if (stats) {  // one atomic per (warp, channel) for the whole kernel instead of one per tile
+      float* const r0 = BZ ? P.bz_s1 : P.sum;    // sum x (fprop) / sum dz (dz epilogue)
+      float* const r1 = BZ ? P.bz_s0 : P.sumsq;  // sum x^2 (fprop) / sum dz*(y-mean)
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        atomicAdd(P.sum + n0 + (half * NQ + q) * 32 + lane, stat_s[q]);
-        atomicAdd(P.sumsq + n0 + (half * NQ + q) * 32 + lane, stat_q[q]);
+        atomicAdd(r0 + n0 + (half * NQ + q) * 32 + lane, stat_s[q]);
+        atomicAdd(r1 + n0 + (half * NQ + q) * 32 + lane, stat_q[q]);
       }
     }
   }
@@ -407,12 +459,12 @@ int map_w(CUtensorMap* m, const void* base, long rows, long cols, int box_rows) 
   return 0;
 }
 
-template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false>
+template <int BN, bool DGRAD, bool RESIDENT, bool STEM = false, bool BZ = false>
 int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cudaStream_t s) {
   using C = HCfg<BN, DGRAD, RESIDENT>;
   const int resident_bytes = RESIDENT ? p.chunks * (STEM ? 1 : 9) * C::B_TILE : 0;
   const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
-  constexpr int kStatic = kEpiWarps * 16 * 36 * 4 + 64;  // epilogue reduction scratch (static shared memory)
+  constexpr int kStatic = kEpiWarps * 16 * 36 * 4 + 64 + (BZ ? 3 * BN * 4 : 16);  // epilogue scratch (static shared memory)
   int a_stages = (int)((227 * 1024 - 1024 - 512 - kStatic - b_bytes) / PATCH_STRIDE);
   if (a_stages > 6) a_stages = 6;
   if (p.sum == nullptr && p.sumsq != nullptr) a_stages = 2;  // (debug hook, unused)
@@ -421,19 +473,19 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
     fd_set_error("conv_halo: shared memory budget exceeded", __FILE__, __LINE__);
     return -1;
   }
-  FD_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, RESIDENT, STEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  FD_CUDA_CHECK(cudaFuncSetAttribute(conv_halo_kernel<BN, DGRAD, RESIDENT, STEM, BZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int grid = h_sms / p.n_tiles * p.n_tiles;
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
   if (grid < p.n_tiles) grid = p.n_tiles;
-  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM><<<grid, kThreadsConv, smem, s>>>(a, b, p, resident_bytes, a_stages);
+  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM, BZ><<<grid, kThreadsConv, smem, s>>>(a, b, p, resident_bytes, a_stages);
   FD_LAUNCH_OK();
   return 0;
 }
 
 template <bool DGRAD>
 int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, float* sum, float* sumsq, int N, int H,
-                     int W, int Cin, int Cout, int wcols, int variant, cudaStream_t s) {
+                     int W, int Cin, int Cout, int wcols, int variant, cudaStream_t s, const FdBnEpilogue* bz = nullptr) {
   // in: [N,H,W,Cin] (x or dy), out: [N,H,W,Cout]; weight matrix rows: K_filter, cols: 9*C_filter (wcols = C_filter)
   if (h_init()) return -1;
   if (Cin % 64 || Cout % 64) {
@@ -445,6 +497,10 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, 
   p.tiles_h = (H + TH - 1) / TH; p.tiles_w = (W + TW - 1) / TW;
   p.m_tiles = N * p.tiles_h * p.tiles_w;
   p.wcols = wcols; p.out = out; p.sum = sum; p.sumsq = sumsq; p.add = add;
+  if (bz) {
+    p.bz_y = bz->y; p.bz_out = bz->out; p.bz_mean = bz->mean; p.bz_rstd = bz->rstd; p.bz_gamma = bz->gamma;
+    p.bz_beta = bz->beta; p.bz_s0 = bz->s0; p.bz_s1 = bz->s1;
+  }
   p.dbg = variant >> 9; variant &= 255;  // bit 8 = statistics buffers pre-zeroed (fd_conv3x3_fprop), bits 9+ = ablation
   // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
   const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
@@ -464,6 +520,14 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, 
   // fprop: rows = K (filter outputs), box rows = bn ; dgrad: rows = K (reduction), box rows = 64 (N-major tiles)
   const long wrows = DGRAD ? Cin : Cout;
   if (map_w(&mb, w, wrows, 9L * wcols, DGRAD ? 64 : bn)) return -1;
+  if constexpr (DGRAD) {
+    if (bz) {  // dz epilogue: compiled for the shapes that use the halo dgrad (64-channel stage: resident filter slice)
+      if (variant == 1) return launch_halo<64, true, true, false, true>(ma, mb, p, s);
+      if (variant == 3) return launch_halo<128, true, false, false, true>(ma, mb, p, s);
+      fd_set_error("conv3x3_dgrad: dz epilogue needs variant 1 or 3", __FILE__, __LINE__);
+      return -1;
+    }
+  }
   switch (variant) {
     case 1: return launch_halo<64, DGRAD, true>(ma, mb, p, s);
     case 2: return launch_halo<64, DGRAD, false>(ma, mb, p, s);
@@ -858,7 +922,7 @@ int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* s
   }
   return conv3x3_dispatch<false>(x, w, y, nullptr, sum, sumsq, N, H, W, C, K, C, variant, s);
 }
-int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K,
-                     int variant, cudaStream_t s) {
-  return conv3x3_dispatch<true>(dy, w, dx, add, nullptr, nullptr, N, H, W, K, C, C, variant, s);
+int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, const FdBnEpilogue* bz, int N, int H, int W,
+                     int C, int K, int variant, cudaStream_t s) {
+  return conv3x3_dispatch<true>(dy, w, dx, add, nullptr, nullptr, N, H, W, K, C, C, variant, s, bz);
 }

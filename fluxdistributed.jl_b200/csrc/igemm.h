@@ -31,8 +31,8 @@ int fd_conv_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W,
 // halo-tile 3x3 / stride-1 / pad-1 kernels (conv_halo_sm100.cu); variant 0 = auto
 int fd_conv3x3_fprop(const void* x, const void* w, void* y, float* sum, float* sumsq, int N, int H, int W, int C, int K,
                      int variant, cudaStream_t s);
-int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, int N, int H, int W, int C, int K,
-                     int variant, cudaStream_t s);
+int fd_conv3x3_dgrad(const void* dy, const void* w, void* dx, const void* add, const FdBnEpilogue* bz, int N, int H, int W,
+                     int C, int K, int variant, cudaStream_t s);
 int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int C, int K, int splits,
                      cudaStream_t s);
 // stem: 7x7/2 conv as a 4x4/1 conv over the space-to-depth input (conv_halo_sm100.cu)

@@ -610,6 +610,169 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
 }
 
 // ---------------------------------------------------------------------------------------------
+// Stem tail backward in one launch: max-pool backward (arg-max gather) + ReLU mask + BN backward (round 2).
+// The forward fuses BN + ReLU + 3x3/2 max-pool (bn_relu_pool3s2_kernel); its backward used to be maxpool_bwd_idx
+// (writes the full-resolution gradient, 154 MB at batch 96) followed by bn_bwd_fused (reads it twice).  Here the
+// full-resolution gradient is never materialised: both passes of the grid-barrier BN backward rebuild it on the fly
+// from the pooled gradient and the arg-max bytes (<= 2x2 windows of 24 bytes each per output vector, L1/L2 hits).
+// ---------------------------------------------------------------------------------------------
+FD_DEVINL V8 pool3s2_gather(const uint8_t* __restrict__ idx, const bf16* __restrict__ g, int n, int h, int w, int cv, int C8,
+                            int P, int Q) {
+  // windows (p, q) of the 3x3 / stride-2 / pad-1 pool that contain pixel (h, w): p in [ceil((h-1)/2), floor((h+1)/2)]
+  const int p_lo = max(0, h >> 1), p_hi = min(P - 1, (h + 1) >> 1);
+  const int q_lo = max(0, w >> 1), q_hi = min(Q - 1, (w + 1) >> 1);
+  uint2 pk[4];
+  V8 dv[4];
+  uint32_t pos[4];
+  bool ok[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int p = p_lo + (u >> 1), q = q_lo + (u & 1);
+    ok[u] = (p <= p_hi) && (q <= q_hi);
+    if (ok[u]) {
+      const long oi = (((long)n * P + p) * Q + q) * C8 + cv;
+      pos[u] = (uint32_t)((h - (p * 2 - 1)) * 3 + (w - (q * 2 - 1)));
+      pk[u] = *reinterpret_cast<const uint2*>(idx + oi * 8);
+      dv[u] = ldg8(g + oi * 8);
+    }
+  }
+  __nv_bfloat162 acc[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) acc[e] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    if (!ok[u]) continue;
+    const uint32_t rep = pos[u] * 0x01010101u;
+    const uint32_t m_lo = __vcmpeq4(pk[u].x, rep), m_hi = __vcmpeq4(pk[u].y, rep);  // 0xFF per matching channel
+    const uint32_t w0 = dv[u].u[0] & __byte_perm(m_lo, 0, 0x1100), w1 = dv[u].u[1] & __byte_perm(m_lo, 0, 0x3322);
+    const uint32_t w2 = dv[u].u[2] & __byte_perm(m_hi, 0, 0x1100), w3 = dv[u].u[3] & __byte_perm(m_hi, 0, 0x3322);
+    acc[0] = __hadd2(acc[0], *reinterpret_cast<const __nv_bfloat162*>(&w0));
+    acc[1] = __hadd2(acc[1], *reinterpret_cast<const __nv_bfloat162*>(&w1));
+    acc[2] = __hadd2(acc[2], *reinterpret_cast<const __nv_bfloat162*>(&w2));
+    acc[3] = __hadd2(acc[3], *reinterpret_cast<const __nv_bfloat162*>(&w3));
+  }
+  V8 o;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) o.u[e] = *reinterpret_cast<const uint32_t*>(&acc[e]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_pool_fused_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ g, const bf16* __restrict__ y,
+                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         bf16* __restrict__ dy, float* __restrict__ accbuf, GridSync gs, int N, int H, int W, int C, int P,
+                         int Q) {
+  constexpr int U = 2;
+  extern __shared__ float smem[];
+  __shared__ unsigned s_gen0;
+  const int C8 = C / 8;
+  const int RL = 256 / C8;
+  const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
+  const long M = (long)N * H * W;
+  if (threadIdx.x == 0) s_gen0 = *reinterpret_cast<volatile unsigned*>(gs.gen);
+  float acc[2][8];  // sum dz*(y-mean), sum dz
+  float mu[8], gsc[8], gsh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    acc[0][j] = acc[1][j] = 0.f;
+    mu[j] = mean[cv * 8 + j];
+    gsc[j] = gamma[cv * 8 + j] * rstd[cv * 8 + j];
+    gsh[j] = beta[cv * 8 + j] - mu[j] * gsc[j];
+  }
+  if (rl < RL) {
+    const long per = (M + gridDim.x - 1) / gridDim.x;
+    const long r0 = (long)blockIdx.x * per, r1 = (r0 + per < M) ? r0 + per : M;
+    for (long r = r0 + rl; r < r1; r += (long)U * RL) {
+      V8 a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long rr = r + (long)u * RL;
+        if (rr < r1) {
+          const uint32_t t = (uint32_t)rr;
+          const int w = (int)(t % (uint32_t)W), h = (int)((t / (uint32_t)W) % (uint32_t)H), n = (int)(t / (uint32_t)(W * H));
+          b[u] = ldg8(y + rr * C + cv * 8);
+          a[u] = pool3s2_gather(idx, g, n, h, w, cv, C8, P, Q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (r + (long)u * RL < r1) {
+          float d[8], yy[8];
+          unpack8(a[u], d);
+          unpack8(b[u], yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float pre = yy[j] * gsc[j] + gsh[j];
+            const float dz = (pre > 0.f) ? d[j] : 0.f;
+            acc[0][j] += dz * (yy[j] - mu[j]);
+            acc[1][j] += dz;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const unsigned gen0 = s_gen0;
+  float* accum = accbuf + (size_t)(gen0 & 1) * 2 * C;
+  float* other = accbuf + (size_t)((gen0 & 1) ^ 1) * 2 * C;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) other[c] = 0.f;
+  block_accumulate2(acc, C8, cv, rl, RL, smem, accum);
+  grid_barrier(gs, gen0);
+  float* ka = smem;
+  float* kb = smem + C;
+  float* kc = smem + 2 * C;
+  float* ksh = smem + 3 * C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float g_ = gamma[c], r_ = rstd[c], m_ = mean[c];
+    const float dg = __ldcg(accum + c) * r_, db = __ldcg(accum + C + c);
+    if (blockIdx.x == 0) {
+      dgamma[c] = dg;
+      dbeta[c] = db;
+    }
+    ka[c] = g_ * r_;
+    kb[c] = -g_ * r_ * r_ * dg * invM;
+    kc[c] = g_ * r_ * (m_ * r_ * dg * invM - db * invM);
+    ksh[c] = beta[c] - m_ * g_ * r_;
+  }
+  __syncthreads();
+  const long total = M * C8;
+  const long stride = (long)gridDim.x * blockDim.x;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += U * stride) {
+    V8 a[U], b[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        int c_, w, h, n;
+        split4(ii, C8, W, H, c_, w, h, n);
+        b[u] = ldg8(y + ii * 8);
+        a[u] = pool3s2_gather(idx, g, n, h, w, c_, C8, P, Q);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long ii = i + u * stride;
+      if (ii < total) {
+        const int ch = (int)(ii % C8) * 8;
+        float d[8], yy[8];
+        unpack8(a[u], d);
+        unpack8(b[u], yy);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float pre = yy[j] * ka[ch + j] + ksh[ch + j];
+          const float dz = (pre > 0.f) ? d[j] : 0.f;
+          d[j] = ka[ch + j] * dz + kb[ch + j] * yy[j] + kc[ch + j];
+        }
+        stg8(dy + ii * 8, pack8(d));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Second (and only remaining) pass of the BN backward when the producer of the output gradient already applied the
 // ReLU mask and reduced sum(dz), sum(dz*(y-mean)) in its epilogue (igemm "dz epilogue"):
 //   dy = g*rstd * dz - g*rstd^2*dgamma/M * (y-mean)... folded into  ka*dz + kb*y + kc.
@@ -1524,6 +1687,29 @@ int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const floa
   bn_bwd_fused_kernel<<<grid, 256, smem, s>>>(
       reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
       rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), accbuf, gs, M, C, relu);
+  FD_LAUNCH_OK();
+  return 0;
+}
+
+// stem tail: pooled gradient g [N,P,Q,C] + arg-max bytes idx -> dy [N,H,W,C] of the stem conv output, dgamma, dbeta
+int fd_bn_bwd_pool_fused(const void* idx, const void* g, const void* y, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* ws, int N,
+                         int H, int W, int C, cudaStream_t s) {
+  const int C8 = C / 8;
+  const int RL = C8 ? 256 / C8 : 0;
+  if (C % 8 || RL == 0) { fd_set_error("bn_bwd_pool_fused: unsupported C", __FILE__, __LINE__); return -1; }
+  const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
+  const long M = (long)N * H * W;
+  if (M * C8 >= 0x100000000LL) { fd_set_error("bn_bwd_pool_fused: tensor too large", __FILE__, __LINE__); return -1; }
+  size_t smem = (size_t)RL * C * 2 * sizeof(float);
+  if (smem < (size_t)5 * C * sizeof(float)) smem = 5 * C * sizeof(float);
+  const int grid = bn_fused_grid((const void*)bn_bwd_pool_fused_kernel, smem, M, C);
+  if (grid < 1) { fd_set_error("bn_bwd_pool_fused: occupancy query failed", __FILE__, __LINE__); return -1; }
+  GridSync gs{reinterpret_cast<unsigned*>(ws), reinterpret_cast<unsigned*>(ws) + 1};
+  float* accbuf = reinterpret_cast<float*>(ws) + 4;
+  bn_bwd_pool_fused_kernel<<<grid, 256, smem, s>>>(
+      reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(g), reinterpret_cast<const bf16*>(y), mean, rstd,
+      gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), accbuf, gs, N, H, W, C, P, Q);
   FD_LAUNCH_OK();
   return 0;
 }

@@ -48,6 +48,9 @@ inline size_t fd_bn_ws_bytes(int C) { return 16 + (size_t)8 * C * sizeof(float);
 int fd_bn_fwd_fused(const void* y, const void* res, void* out, const float* gamma, const float* beta, float* run_mean,
                     float* run_var, float* save_mean, float* save_rstd, void* ws, long M, int C, float eps,
                     float momentum, int relu, cudaStream_t s);
+int fd_bn_bwd_pool_fused(const void* idx, const void* g, const void* y, const float* mean, const float* rstd,
+                         const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* ws, int N,
+                         int H, int W, int C, cudaStream_t s);
 int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, void* ws,
                     long M, int C, int relu, cudaStream_t s);

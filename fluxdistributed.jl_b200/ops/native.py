@@ -107,12 +107,23 @@ def conv3x3_fprop(x: torch.Tensor, w: torch.Tensor, stats=False, variant: int = 
     return (from_nhwc(y), s, ss) if stats else from_nhwc(y)
 
 
-def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, variant: int = 0, add: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``add`` (same shape as the result) is summed into dx in the epilogue (fused residual-gradient accumulation)."""
+def _bn_epi_list(bn_epi, device):
+    y_, out_, mean_, rstd_, gamma_, beta_, s0_, s1_ = bn_epi
+    return [nhwc(y_), nhwc(out_) if out_ is not None else torch.empty(0, dtype=BF16, device=device), mean_, rstd_,
+            gamma_, beta_, s0_, s1_]
+
+
+def conv3x3_dgrad(dy: torch.Tensor, w: torch.Tensor, variant: int = 0, add: Optional[torch.Tensor] = None,
+                  bn_epi=None) -> torch.Tensor:
+    """``add`` (same shape as the result) is summed into dx in the epilogue (fused residual-gradient accumulation).
+    ``bn_epi``: dz epilogue as in :func:`conv_dgrad` (ReLU mask + BN-backward sums of the producing BN layer)."""
     dyh, wk = nhwc(dy), krsc(w)
     n, h, ww, _ = dyh.shape
     dx = torch.empty(n, h, ww, wk.shape[3], dtype=BF16, device=dy.device)
-    _ext().conv3x3_dgrad(dyh, wk, dx, variant, None if add is None else nhwc(add))
+    epi = None if bn_epi is None else _bn_epi_list(bn_epi, dy.device)
+    if epi is not None and variant == 0:
+        variant = 1 if wk.shape[3] == 64 and wk.shape[0] == 64 else 3
+    _ext().conv3x3_dgrad(dyh, wk, dx, variant, None if add is None else nhwc(add), epi)
     return from_nhwc(dx)
 
 
@@ -373,6 +384,22 @@ def bn_fwd_fused(y, gamma, beta, eps, ws, residual=None, relu=True, running_mean
     return from_nhwc(out), mean, rstd
 
 
+POOL_BWD_FUSED = os.environ.get("FLUXDIST_POOL_BWD_FUSED", "1") != "0"
+HALO_DZ = os.environ.get("FLUXDIST_HALO_DZ", "1") != "0"  # dz epilogue in the halo dgrad (64-channel stage)
+
+
+def bn_bwd_pool_fused(idx, g, y, mean, rstd, gamma, beta, ws, dgamma=None, dbeta=None):
+    """Backward of ``bn_relu_pool`` in one launch: ``g`` is the gradient of the POOLED activation ([N,C,P,Q]), ``idx`` the
+    arg-max bytes of the forward; returns (dy w.r.t. the raw conv output ``y``, dgamma, dbeta)."""
+    yh = nhwc(y)
+    c = y.shape[1]
+    dy = torch.empty_like(yh)
+    dgamma = dgamma if dgamma is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    dbeta = dbeta if dbeta is not None else torch.empty(c, dtype=torch.float32, device=y.device)
+    _ext().bn_bwd_pool_fused(idx, nhwc(g), yh, mean, rstd, gamma, beta, dgamma, dbeta, dy, ws)
+    return from_nhwc(dy), dgamma, dbeta
+
+
 def bn_bwd_fused(dout, y, out, mean, rstd, gamma, beta, ws, relu=True, want_dres=False, dgamma=None, dbeta=None):
     yh = nhwc(y)
     c = y.shape[1]
@@ -546,12 +573,19 @@ class _ConvBNAct(torch.autograd.Function):
         x, wl, y, out, mean, rstd, gamma, beta = ctx.saved_tensors
         relu, stride, pad, has_res, tc, w_shape, x_shape, k3, stem = ctx.cfg
         dout = dout if dout.dtype == BF16 else dout.to(BF16)
-        if ctx.pool_idx is not None:  # route the pooled gradient back to full resolution (gather, no atomics)
+        pool_fused = ctx.pool_idx is not None and ctx.bn_ws is not None and POOL_BWD_FUSED and relu and not has_res
+        if ctx.pool_idx is not None and not pool_fused:  # route the pooled gradient back to full resolution (gather)
             n_, c_, h_, w_ = y.shape
             dfull = torch.empty(n_, h_, w_, c_, dtype=BF16, device=y.device)
             _ext().maxpool_bwd_idx(ctx.pool_idx, nhwc(dout), dfull, 3, 2, 1)
             dout = from_nhwc(dfull)
-        if ctx.own_link is not None and ctx.own_link.pop("dz", False):
+        if pool_fused:
+            # stem tail: max-pool backward + ReLU mask + BN backward in ONE launch; the full-resolution gradient of
+            # the pooled activation is never written (bn_bwd_pool_fused_kernel)
+            dy, dgamma, dbeta = bn_bwd_pool_fused(ctx.pool_idx, dout, y, mean, rstd, gamma, beta, ctx.bn_ws,
+                                                  ctx.g_gradbuf, ctx.b_gradbuf)
+            dres = None
+        elif ctx.own_link is not None and ctx.own_link.pop("dz", False):
             # dout is already the masked gradient dz; its sums sit in the workspace (reduced by the consumer's dgrad)
             c_ = y.shape[1]
             wf = ctx.bn_ws.view(torch.float32)
@@ -578,7 +612,15 @@ class _ConvBNAct(torch.autograd.Function):
                 ctx.add_link["late"] = True  # the projection has not run yet: it must return its own dx
             park = ctx.park_link
             if k3 and _halo_fprop_ok(w_shape[0], w_shape[1], x_shape[2]):
-                dx = conv3x3_dgrad(dy, wl, add=add)
+                epi = None
+                src = ctx.src_link
+                if HALO_DZ and src is not None and "bn" in src and addc is None:
+                    y_s, out_s, mean_s, rstd_s, gamma_s, beta_s, ws_s = src["bn"]
+                    cs = y_s.shape[1]
+                    wfs = ws_s.view(torch.float32)
+                    epi = (y_s, out_s, mean_s, rstd_s, gamma_s, beta_s, wfs[4 + 6 * cs: 4 + 7 * cs], wfs[4 + 7 * cs: 4 + 8 * cs])
+                    src["dz"] = True
+                dx = conv3x3_dgrad(dy, wl, add=add, bn_epi=epi)
             elif tc and park is not None and not park.get("late") and stride == 2 and w_shape[2] == 1 \
                     and _s2_native_ok(x_shape[2], x_shape[3], 1, 1, pad):
                 dyh = nhwc(dy)

@@ -35,16 +35,18 @@ MAX_GRID = 296
 
 
 def _bucket_fracs(world: int = 2) -> tuple:
-    """Bucket plan: cumulative size fractions (in backward order) after which a bucket is cut.  The default gives
-    ResNet-34 three buckets on multi-GPU runs: layer4 + fc (62 % of the bytes, ready first), layer3 (31 %), the rest +
-    all 1-D parameters.  A single GPU keeps ONE bucket at the end of the backward pass: there is nothing to exchange,
-    and the update-only kernel runs at 91 % of the copy bandwidth on the whole GPU but competes with the backward pass
-    when launched early on a bounded grid (measured, gpurun_out/r2ab: 19.8k img/s with one bucket, 19.4k with three).
-    ``FLUXDIST_BUCKETS=0`` forces one bucket, ``FLUXDIST_BUCKETS=0.55,0.9`` forces the cuts."""
+    """Bucket plan: cumulative size fractions (in backward order) after which a bucket is cut, e.g.
+    ``FLUXDIST_BUCKETS=0.55,0.9`` gives ResNet-34 three buckets — layer4 + fc (62 % of the bytes, ready first), layer3
+    (31 %), the rest + all 1-D parameters — each launched on the communication stream from a gradient-ready hook while
+    the backward pass of the earlier layers still runs.
+
+    Default: ONE bucket at the end of the backward pass.  Measured on B200 (gpurun_out/r2ab, r2ab2; ResNet-34, batch
+    96/GPU): 1 GPU 19.8k img/s with one bucket vs 19.4k with three early buckets; 2 GPUs 39.3k (4.887 ms/step, +53 us
+    over the 1-GPU step) vs 38.3k (early grid 32) / 39.1k (early grid 64).  The exchange kernel moves its bytes with SM
+    instructions (peer loads / multimem.ld_reduce), so running it early takes issue slots and CTA slots from the
+    backward pass it overlaps with — more than the ~50-100 us of exposed exchange time it hides at these sizes."""
     env = os.environ.get("FLUXDIST_BUCKETS")
-    if env is None:
-        return () if world <= 1 else (0.55, 0.9)
-    if env.strip() in ("", "0", "off", "none"):
+    if env is None or env.strip() in ("", "0", "off", "none"):
         return ()
     return tuple(float(x) for x in env.split(","))
 
