@@ -396,18 +396,25 @@ def main():
         fd.nn.set_backend("torch")
         m = model.to(dev).to(memory_format=torch.channels_last)
         tuned = args.impl == "ddp_tuned"
-        ddp = DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True, static_graph=tuned) if world > 1 else m
-        if args.opt == "momentum":
-            topt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, foreach=not tuned, fused=tuned or None)
-        else:
-            topt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=tuned)
-        x_static = torch.zeros(B, hw, hw, 3, dtype=torch.uint8, device=dev)
-        y_static = torch.zeros(B, dtype=torch.int64, device=dev)
-        x_static.copy_(host_x)
-        y_static.copy_(host_y)
-        mean = torch.tensor(fd.data.MEAN, device=dev).view(1, 3, 1, 1)
-        std = torch.tensor(fd.data.STD, device=dev).view(1, 3, 1, 1)
-        out_loss = torch.zeros((), device=dev)
+        side = torch.cuda.Stream() if tuned else None
+        if tuned:
+            os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+            side.wait_stream(torch.cuda.current_stream())
+        # PyTorch's recipe for capturing DDP in a CUDA graph: construct DDP, the optimiser and run >= 11 warm-up
+        # iterations in a side-stream context, then capture the whole iteration on that stream
+        with (torch.cuda.stream(side) if tuned else contextlib.nullcontext()):
+            ddp = DDP(m, device_ids=[local_rank], gradient_as_bucket_view=True, static_graph=tuned) if world > 1 else m
+            if args.opt == "momentum":
+                topt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, foreach=not tuned, fused=tuned or None)
+            else:
+                topt = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True, capturable=tuned)
+            x_static = torch.zeros(B, hw, hw, 3, dtype=torch.uint8, device=dev)
+            y_static = torch.zeros(B, dtype=torch.int64, device=dev)
+            x_static.copy_(host_x)
+            y_static.copy_(host_y)
+            mean = torch.tensor(fd.data.MEAN, device=dev).view(1, 3, 1, 1)
+            std = torch.tensor(fd.data.STD, device=dev).view(1, 3, 1, 1)
+            out_loss = torch.zeros((), device=dev)
 
         def body():
             x = ((x_static.permute(0, 3, 1, 2).float() / 255.0 - mean) / std).contiguous(memory_format=torch.channels_last)
@@ -420,22 +427,24 @@ def main():
 
         graph = None
         if tuned:
-            # whole DDP step (forward, backward with NCCL bucket all-reduces, fused optimiser) in one CUDA graph
             try:
-                s = torch.cuda.Stream()
-                s.wait_stream(torch.cuda.current_stream())
-                with torch.cuda.stream(s):
-                    for _ in range(11):  # DDP needs >= 11 warm-up iterations on the capture stream before capture
+                with torch.cuda.stream(side):
+                    for _ in range(11):
                         body()
-                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.current_stream().wait_stream(side)
                 torch.cuda.synchronize()
                 graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
+                with torch.cuda.graph(graph, stream=side):
                     body()
+                torch.cuda.synchronize()
                 cuda_graph = True
             except Exception as e:  # noqa: BLE001 - report the eager number, flagged
                 graph = None
                 comm_info = {"graph_capture_failed": str(e)[:200]}
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
 
         def run_step():
             if graph is not None:

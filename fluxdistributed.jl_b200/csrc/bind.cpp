@@ -409,6 +409,29 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("normalize_u8", &normalize_u8);
   m.def("cast_f32_bf16", &cast_f32_bf16);
   m.def("small_gemm", &small_gemm);
+  // direct NHWC convolution (x [N,H,W,C], w [K,R,S,C], y [N,P,Q,K], all bf16; dw fp32 addressed by element strides)
+  m.def("direct_conv_fprop", [](at::Tensor x, at::Tensor w, c10::optional<at::Tensor> bias, at::Tensor y, int stride, int pad) {
+    want(x, at::kBFloat16, "x"); want(w, at::kBFloat16, "w"); want(y, at::kBFloat16, "y");
+    c10::cuda::CUDAGuard guard(x.device());
+    check(fd_direct_conv_fprop(x.data_ptr(), w.data_ptr(), optf(bias), y.data_ptr(), (int)x.size(0), (int)x.size(1), (int)x.size(2),
+                               (int)x.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
+          "direct_conv_fprop");
+  });
+  m.def("direct_conv_dgrad", [](at::Tensor dy, at::Tensor w, at::Tensor dx, int stride, int pad) {
+    want(dy, at::kBFloat16, "dy"); want(w, at::kBFloat16, "w"); want(dx, at::kBFloat16, "dx");
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_direct_conv_dgrad(dy.data_ptr(), w.data_ptr(), dx.data_ptr(), (int)dx.size(0), (int)dx.size(1), (int)dx.size(2),
+                               (int)dx.size(3), (int)w.size(0), (int)w.size(1), (int)w.size(2), stride, pad, cur_stream()),
+          "direct_conv_dgrad");
+  });
+  m.def("direct_conv_wgrad", [](at::Tensor dy, at::Tensor x, at::Tensor dw, c10::optional<at::Tensor> dbias, int R, int S, int stride,
+                                int pad, long sk, long sr, long ss, long sc) {
+    want(dy, at::kBFloat16, "dy"); want(x, at::kBFloat16, "x"); want(dw, at::kFloat, "dw");
+    c10::cuda::CUDAGuard guard(dy.device());
+    check(fd_direct_conv_wgrad(dy.data_ptr(), x.data_ptr(), dw.data_ptr<float>(), optf(dbias), (int)x.size(0), (int)x.size(1),
+                               (int)x.size(2), (int)x.size(3), (int)dy.size(3), R, S, stride, pad, sk, sr, ss, sc, cur_stream()),
+          "direct_conv_wgrad");
+  });
   m.def("bias_add", &bias_add);
   m.def("colsum", &colsum);
   m.def("enable_peer_access", &enable_peer_access);

@@ -52,6 +52,26 @@ FD_DEVINL float warp_max(float v) {
   return v;
 }
 
+// Column sums of a 32x32 fp32 block held one row per lane (v[c] = this lane's value of column c): a transpose-reduce
+// butterfly on the shuffle network — after it, lane L holds the sum over all 32 rows of column L.  ~125 instructions
+// and NO shared-memory traffic: the tcgen05 main loops are bound by shared-memory operand bandwidth (an M=128,K=16 MMA
+// costs max(80, N/2) clk, scripts/probe_mma_rate.py), so every byte the epilogue warps move through shared memory
+// slows the MMAs of the next tile — the round-2 measurement behind switching the statistics / dz epilogues from the
+// shared-memory tile reduction (fewer instructions) back to shuffles.  Destroys v.
+FD_DEVINL float warp_colsum_shfl(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float keep = up ? v[j + off] : v[j];
+      const float send = up ? v[j] : v[j + off];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // ------------------------------------------------------------------ system-scope flags (cross-GPU barriers)
 FD_DEVINL void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");

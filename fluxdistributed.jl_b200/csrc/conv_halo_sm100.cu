@@ -296,11 +296,14 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int acc = 0;
     uint32_t accph = 0;
     const bool stats = ((!DGRAD) && P.sum != nullptr) || BZ;
-    __shared__ __align__(16) float colred_all[kEpiWarps * 16 * 36];
-    float* const colred = colred_all + (warp - 2) * 16 * 36;
-    float stat_s[NQ], stat_q[NQ];
+    // statistics: every thread accumulates ITS row's contribution to the 32 columns of each chunk over all tiles of the
+    // CTA in registers (one FADD + one FFMA per element, nothing crosses lanes); the 32 rows of a warp are summed once,
+    // after the last tile.  No shared-memory traffic while the MMAs run (they are bound by shared-memory bandwidth).
+    float acc_s[NQ][32], acc_q[NQ][32];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) stat_s[q] = stat_q[q] = 0.f;
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc_s[q][j] = acc_q[q][j] = 0.f;
     for (int mt = m_first; mt < P.m_tiles; mt += m_step) {
       const int n = mt / (P.tiles_h * P.tiles_w);
       const int rem = mt - n * (P.tiles_h * P.tiles_w);
@@ -366,9 +369,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               }
             }
           }
-          float unused = 0.f;
-          halo_column_sums(f, colred, lane, stat_s[q], unused);
-          halo_column_sums(qv, colred, lane, stat_q[q], unused);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc_s[q][j] += f[j];
+            acc_q[q][j] += qv[j];
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 2) v[j >> 1] = pack_bf16x2(f[j], f[j + 1]);
         } else {
@@ -386,7 +391,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           for (int j = 0; j < 4; ++j)
             *reinterpret_cast<uint4*>(orow + c0 + j * 8) = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
         }
-        if (stats && !BZ) halo_column_sums(f, colred, lane, stat_s[q], stat_q[q]);  // lane L: column c0+L over this CTA's tiles
+        if (stats && !BZ) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            acc_s[q][j] += f[j];
+            acc_q[q][j] = fmaf(f[j], f[j], acc_q[q][j]);
+          }
+        }
       }
       acc ^= 1;
       if (acc == 0) accph ^= 1;
@@ -396,8 +407,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       float* const r1 = BZ ? P.bz_s0 : P.sumsq;  // sum x^2 (fprop) / sum dz*(y-mean)
 #pragma unroll
       for (int q = 0; q < NQ; ++q) {
-        atomicAdd(r0 + n0 + (half * NQ + q) * 32 + lane, stat_s[q]);
-        atomicAdd(r1 + n0 + (half * NQ + q) * 32 + lane, stat_q[q]);
+        const float s_ = warp_colsum_shfl(acc_s[q], lane);  // lane L: column c0+L summed over the warp's 32 rows
+        const float q_ = warp_colsum_shfl(acc_q[q], lane);
+        atomicAdd(r0 + n0 + (half * NQ + q) * 32 + lane, s_);
+        atomicAdd(r1 + n0 + (half * NQ + q) * 32 + lane, q_);
       }
     }
   }
@@ -464,7 +477,7 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
   using C = HCfg<BN, DGRAD, RESIDENT>;
   const int resident_bytes = RESIDENT ? p.chunks * (STEM ? 1 : 9) * C::B_TILE : 0;
   const int b_bytes = RESIDENT ? resident_bytes : C::B_STAGES * C::B_TILE;
-  constexpr int kStatic = kEpiWarps * 16 * 36 * 4 + 64 + (BZ ? 3 * BN * 4 : 16);  // epilogue scratch (static shared memory)
+  constexpr int kStatic = 64 + (BZ ? 3 * BN * 4 : 16);  // static shared memory (dz-epilogue coefficients)
   int a_stages = (int)((227 * 1024 - 1024 - 512 - kStatic - b_bytes) / PATCH_STRIDE);
   if (a_stages > 6) a_stages = 6;
   if (p.sum == nullptr && p.sumsq != nullptr) a_stages = 2;  // (debug hook, unused)
@@ -504,7 +517,7 @@ int conv3x3_dispatch(const void* in, const void* w, void* out, const void* add, 
   p.dbg = variant >> 9; variant &= 255;  // bit 8 = statistics buffers pre-zeroed (fd_conv3x3_fprop), bits 9+ = ablation
   // variant: 0 = auto, 1 = BN64 resident, 2 = BN64 streamed, 3 = BN128 streamed, 4 = BN128 resident
   const long res64 = (long)p.chunks * 9 * 64 * 128, res128 = (long)p.chunks * 9 * 128 * 128;
-  const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048 - (kEpiWarps * 16 * 36 * 4 + 64);
+  const long budget = 227 * 1024 - 3 * PATCH_STRIDE - 2048 - 1024;
   if (variant == 0) {
     if (res64 <= budget) variant = 1;
     else variant = (Cout % 128 == 0) ? 3 : 2;

@@ -112,6 +112,22 @@ FD_DEVINL void warp_column_sums_smem(const float (&f)[32], float* buf, int lane,
   sumsq += (b[0] + b[1]) + (b[2] + b[3]);
 }
 
+// Shuffle-network variant (no shared-memory traffic, see common.cuh::warp_colsum_shfl): used by the eight-warp
+// epilogues, where the extra instructions are spread over two warps per scheduler and the shared-memory bandwidth is
+// what the MMAs of the next tile need.  want_sq: also accumulate the sum of squares.
+template <bool WANT_SQ>
+FD_DEVINL void warp_column_sums_shfl(const float (&f)[32], int lane, float& sum, float& sumsq) {
+  float a[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) a[j] = f[j];
+  sum += warp_colsum_shfl(a, lane);
+  if (WANT_SQ) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = f[j] * f[j];
+    sumsq += warp_colsum_shfl(a, lane);
+  }
+}
+
 // E8: eight epilogue warps (two per SM sub-partition, BN/2 columns each) instead of four.  One warp per scheduler issues
 // its dependent epilogue instructions back to back (IPC ~0.2); a second warp on the same scheduler fills those slots.
 // One operand stage is given up for the larger per-warp reduction scratch.
@@ -129,7 +145,7 @@ struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;       // 8/16/32 KB
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr bool kStats = (MODE == 1 /*FPROP*/) || BZ;
-  static constexpr int kColredFloats = kStats ? kEpiWarps * 16 * 36 : 4;
+  static constexpr int kColredFloats = (kStats && !E8) ? kEpiWarps * 16 * 36 : 4;  // E8 reduces on the shuffle network
   static constexpr int kBnparFloats = BZ ? kEpiWarps * 3 * (E8 ? BN / 2 : BN) : 4;
   static constexpr int kStaticBytes = (kColredFloats + kBnparFloats) * 4 + 64;
   static constexpr int kBudget = 227 * 1024 - 1024 /*align*/ - 256 /*barriers*/ - kStaticBytes;
@@ -389,7 +405,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
     // per epilogue warp: mean | gamma*rstd | shift of the channels it drains (static shared: plain LDS, no generic loads)
     __shared__ float bnpar_all[C::kBnparFloats];
     __shared__ __align__(16) float colred_all[C::kColredFloats];
-    float* const colred = colred_all + (C::kStats ? (warp - 2) * 16 * 36 : 0);
+    float* const colred = colred_all + ((C::kStats && !E8) ? (warp - 2) * 16 * 36 : 0);
     float* const bnpar = bnpar_all + (bz ? (warp - 2) * 3 * c_count : 0);
     float st_s[c_count / 32], st_q[c_count / 32];  // this lane's channel (c0 + lane) of each 32-column chunk, over this CTA's tiles
 #pragma unroll
@@ -482,14 +498,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
               }
             }
             float unused = 0.f;
-            warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], unused);
-            warp_column_sums_smem(q, colred, lane, st_q[cc0 / 32], unused);
+            if (E8) {
+              warp_column_sums_shfl<false>(f, lane, st_s[cc0 / 32], unused);
+              warp_column_sums_shfl<false>(q, lane, st_q[cc0 / 32], unused);
+            } else {
+              warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], unused);
+              warp_column_sums_smem(q, colred, lane, st_q[cc0 / 32], unused);
+            }
             added = true;  // `add` is already inside v
           } else if (do_stats) {  // rows past M are TMA zero-fill: they add nothing
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], st_q[cc0 / 32]);
+            if (E8) warp_column_sums_shfl<true>(f, lane, st_s[cc0 / 32], st_q[cc0 / 32]);
+            else warp_column_sums_smem(f, colred, lane, st_s[cc0 / 32], st_q[cc0 / 32]);
           }
           if (row < P.M && has_k) {
             if (MODE == MODE_WGRAD) {

@@ -32,6 +32,13 @@ int fd_softmax_ce(const void* logits, const long long* labels, void* dlogits, fl
 int fd_normalize_u8(const void* in, void* out, long pixels, int Cpad, const float* mean, const float* stdv,
                     cudaStream_t s);
 int fd_cast_f32_bf16(const float* in, void* out, long n, cudaStream_t s);
+// direct (CUDA-core) NHWC convolution for channel counts the tensor-core tiles do not cover (direct_conv.cu)
+int fd_direct_conv_fprop(const void* x, const void* w, const float* bias, void* y, int N, int H, int W, int C, int K, int R,
+                         int S, int stride, int pad, cudaStream_t s);
+int fd_direct_conv_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int C, int K, int R, int S, int stride,
+                         int pad, cudaStream_t s);
+int fd_direct_conv_wgrad(const void* dy, const void* x, float* dw, float* dbias, int N, int H, int W, int C, int K, int R,
+                         int S, int stride, int pad, long sk, long sr, long ss, long sc, cudaStream_t s);
 int fd_small_gemm(const void* A, const void* B, float* Cf, void* Cb, int M, int N, int K, long sam, long sak, long sbk,
                   long sbn, long ldc, cudaStream_t s);
 int fd_bias_add(void* y, const float* bias, int M, int N, cudaStream_t s);

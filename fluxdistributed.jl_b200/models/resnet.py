@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 import torch
 from torch import nn
 
-from ..nn.layers import ConvBN, Head, MaxPool
+from ..nn.layers import Conv2dN, ConvBN, Head, LinearN, MaxPool
 
 
 class BasicBlock(nn.Module):
@@ -152,7 +152,7 @@ def ResNet152(nclasses: int = 1000) -> ResNet:
 def resnet_trunk_with_head(nfeat_classes: int = 1000, nout: int = 200) -> nn.Module:
     """The process-mode default model: ``Chain(ResNet().layers[1:end-1], Dense(1000, 200))``
     (``src/sync.jl:215``) — a ResNet-50 whose 1000-way output feeds a 200-way Dense."""
-    return nn.Sequential(ResNet50(nfeat_classes), nn.Linear(nfeat_classes, nout))
+    return nn.Sequential(ResNet50(nfeat_classes), LinearN(nfeat_classes, nout))
 
 
 class TinyConvNet(nn.Module):
@@ -161,9 +161,9 @@ class TinyConvNet(nn.Module):
 
     def __init__(self, nclasses: int = 10, in_hw: int = 32):
         super().__init__()
-        self.conv = nn.Conv2d(3, 3, 7)
+        self.conv = Conv2dN(3, 3, 7)      # nn.Conv2d / nn.Linear subclasses: native kernels on CUDA bf16 inputs
         self.flatten = nn.Flatten()
-        self.dense = nn.Linear(3 * (in_hw - 6) ** 2, nclasses)
+        self.dense = LinearN(3 * (in_hw - 6) ** 2, nclasses)
 
     def forward(self, x):
         return self.dense(self.flatten(self.conv(x)))

@@ -156,6 +156,41 @@ class Flatten(nn.Flatten):
     """``Flux.flatten``."""
 
 
+class Conv2dN(nn.Conv2d):
+    """``nn.Conv2d`` whose CUDA/bf16 path runs this repository's kernels: the tcgen05 implicit GEMM when both channel
+    counts are multiples of 64 (no bias), otherwise the direct CUDA-core convolution (``csrc/direct_conv.cu``) — so
+    the reference's ``Conv((7,7), 3=>3)`` test model no longer falls back to cuDNN.  Same parameters / state dict as
+    ``nn.Conv2d``; CPU and fp32 inputs take the PyTorch path."""
+
+    def forward(self, x):
+        simple = (self.groups == 1 and self.dilation == (1, 1) and self.stride[0] == self.stride[1]
+                  and self.padding[0] == self.padding[1] and isinstance(self.padding, tuple) and x.dim() == 4)
+        if simple and _use_native(x) and x.dtype == torch.bfloat16:
+            from ..ops.native import direct_conv2d
+
+            return direct_conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0])
+        w, b = self.weight, self.bias
+        if x.dtype != w.dtype:
+            w = w.to(x.dtype)
+            b = b.to(x.dtype) if b is not None else None
+        return F.conv2d(x, w, b, self.stride, self.padding, self.dilation, self.groups)
+
+
+class LinearN(nn.Linear):
+    """``nn.Linear`` on this repository's GEMM kernels for CUDA/bf16 inputs (tcgen05 or the small-GEMM kernel)."""
+
+    def forward(self, x):
+        if x.dim() == 2 and _use_native(x) and x.dtype == torch.bfloat16:
+            from ..ops.native import linear
+
+            return linear(x, self.weight, self.bias, getattr(self.weight, "_lowp", None))
+        w, b = self.weight, self.bias
+        if x.dtype != w.dtype:
+            w = w.to(x.dtype)
+            b = b.to(x.dtype) if b is not None else None
+        return F.linear(x, w, b)
+
+
 def Chain(*layers: nn.Module) -> nn.Sequential:
     """``Flux.Chain``."""
     return nn.Sequential(*layers)
@@ -163,13 +198,13 @@ def Chain(*layers: nn.Module) -> nn.Sequential:
 
 def Dense(cin: int, cout: int, bias: bool = True) -> nn.Linear:
     """``Flux.Dense``."""
-    return nn.Linear(cin, cout, bias=bias)
+    return LinearN(cin, cout, bias=bias)
 
 
 def Conv(k, ch, stride: int = 1, pad: int = 0, bias: bool = True) -> nn.Conv2d:
     """``Flux.Conv((k,k), cin=>cout)``; ``ch`` is ``(cin, cout)``."""
     k = k if isinstance(k, int) else k[0]
-    return nn.Conv2d(ch[0], ch[1], k, stride=stride, padding=pad, bias=bias)
+    return Conv2dN(ch[0], ch[1], k, stride=stride, padding=pad, bias=bias)
 
 
 def BatchNorm(c: int) -> nn.BatchNorm2d:

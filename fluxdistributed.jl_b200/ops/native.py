@@ -384,8 +384,12 @@ def bn_fwd_fused(y, gamma, beta, eps, ws, residual=None, relu=True, running_mean
     return from_nhwc(out), mean, rstd
 
 
-POOL_BWD_FUSED = os.environ.get("FLUXDIST_POOL_BWD_FUSED", "1") != "0"
-HALO_DZ = os.environ.get("FLUXDIST_HALO_DZ", "1") != "0"  # dz epilogue in the halo dgrad (64-channel stage)
+# Both fusions below are implemented and tested but measured SLOWER inside the step on B200 (gpurun_out/r2ab, ResNet-34
+# batch 96: 19.84k img/s with neither, 19.45k with the fused stem tail, 19.56k with the halo dz epilogue) and stay off:
+# the fused stem tail repeats the issue-bound arg-max gather in both BN-backward passes, and the halo dgrad of the
+# 64-channel stage is bound by its N=64 MMAs' shared-memory reads, which the longer epilogue competes with.
+POOL_BWD_FUSED = os.environ.get("FLUXDIST_POOL_BWD_FUSED", "0") == "1"
+HALO_DZ = os.environ.get("FLUXDIST_HALO_DZ", "0") == "1"  # dz epilogue in the halo dgrad (64-channel stage)
 
 
 def bn_bwd_pool_fused(idx, g, y, mean, rstd, gamma, beta, ws, dgamma=None, dbeta=None):
@@ -752,6 +756,107 @@ class _GapLinear(torch.autograd.Function):
 def gap_linear(x, w, b, w_lowp=None):
     return _GapLinear.apply(x, w, b, w_lowp, getattr(w, "_gradbuf", None),
                             getattr(b, "_gradbuf", None) if b is not None else None)
+
+
+# --------------------------------------------------------------------------- autograd: plain Conv2d / Linear (any channel count)
+class _DirectConv(torch.autograd.Function):
+    """``Conv2d`` (with bias) on the direct CUDA-core kernels (csrc/direct_conv.cu): the path for channel counts the
+    tensor-core tiles do not cover — the reference's test model ``Conv((7,7),3=>3)`` (test/single_device.jl:117-119)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, stride, pad, w_gradbuf, b_gradbuf):
+        xh = nhwc(x if x.dtype == BF16 else x.to(BF16))
+        wk = w.detach().to(BF16).permute(0, 2, 3, 1).contiguous()  # [K,R,S,C]
+        n, h, ww, c = xh.shape
+        k, r, s_, _ = wk.shape
+        p, q = (h + 2 * pad - r) // stride + 1, (ww + 2 * pad - s_) // stride + 1
+        y = torch.empty(n, p, q, k, dtype=BF16, device=x.device)
+        _ext().direct_conv_fprop(xh, wk, None if b is None else b.detach().float(), y, stride, pad)
+        ctx.save_for_backward(xh, wk)
+        ctx.cfg = (stride, pad, tuple(w.shape), b is not None)
+        ctx.bufs = (w_gradbuf, b_gradbuf)
+        return from_nhwc(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, wk = ctx.saved_tensors
+        stride, pad, w_shape, has_b = ctx.cfg
+        w_gradbuf, b_gradbuf = ctx.bufs
+        dyh = nhwc(dy if dy.dtype == BF16 else dy.to(BF16))
+        e = _ext()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dxh = torch.empty_like(xh)
+            e.direct_conv_dgrad(dyh, wk, dxh, stride, pad)
+            dx = from_nhwc(dxh)
+        k, c, r, s_ = w_shape
+        gw = w_gradbuf if w_gradbuf is not None else torch.zeros(w_shape, dtype=torch.float32, device=dy.device)
+        gb = None
+        if has_b:
+            gb = b_gradbuf if b_gradbuf is not None else torch.zeros(k, dtype=torch.float32, device=dy.device)
+        st = gw.stride()  # element strides of the logical [K,C,R,S] gradient buffer, whatever its memory format
+        e.direct_conv_wgrad(dyh, xh, gw, gb, r, s_, stride, pad, st[0], st[2], st[3], st[1])
+        return (dx, None if w_gradbuf is not None else gw, None if (b_gradbuf is not None or not has_b) else gb,
+                None, None, None, None)
+
+
+def direct_conv2d(x, w, b, stride=1, pad=0):
+    return _DirectConv.apply(x, w, b, stride, pad, getattr(w, "_gradbuf", None),
+                             getattr(b, "_gradbuf", None) if b is not None else None)
+
+
+class _Linear(torch.autograd.Function):
+    """``Linear`` on this repository's GEMM kernels: tcgen05 when the reduction dimension is a multiple of 64, the
+    small-GEMM kernel otherwise (e.g. Dense(2028, 10) of the reference's test model)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, w_lowp, w_gradbuf, b_gradbuf):
+        x2 = (x if x.dtype == BF16 else x.to(BF16)).contiguous()
+        wl = (w_lowp if w_lowp is not None else w.detach().to(BF16)).contiguous()
+        n, kdim = x2.shape
+        m = wl.shape[0]
+        e = _ext()
+        if kdim % 64 == 0:
+            out = gemm_nt(x2, wl)
+        else:
+            out = torch.empty(n, m, dtype=BF16, device=x.device)
+            e.small_gemm(x2, wl, out, n, m, kdim, kdim, 1, 1, kdim)  # out[n,m] = sum_k x[n,k] * w[m,k]
+        if b is not None:
+            e.bias_add(out, b.detach().float())
+        ctx.save_for_backward(x2, wl)
+        ctx.has_b = b is not None
+        ctx.bufs = (w_gradbuf, b_gradbuf)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x2, wl = ctx.saved_tensors
+        w_gradbuf, b_gradbuf = ctx.bufs
+        d = dout.contiguous().to(BF16)
+        n, kdim = x2.shape
+        m = wl.shape[0]
+        e = _ext()
+        gw = torch.zeros(m, kdim, dtype=torch.float32, device=d.device)
+        e.small_gemm(d, x2, gw, m, kdim, n, 1, m, kdim, 1)      # gw[m,k] = sum_n d[n,m] * x[n,k]
+        if w_gradbuf is not None:
+            w_gradbuf.add_(gw)
+        gb = None
+        if ctx.has_b:
+            gb = torch.empty(m, dtype=torch.float32, device=d.device)
+            e.colsum(d, gb)
+            if b_gradbuf is not None:
+                b_gradbuf.add_(gb)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(n, kdim, dtype=BF16, device=d.device)
+            e.small_gemm(d, wl, dx, n, kdim, m, m, 1, kdim, 1)  # dx[n,k] = sum_m d[n,m] * w[m,k]
+        return (dx, None if w_gradbuf is not None else gw, None if (b_gradbuf is not None or not ctx.has_b) else gb,
+                None, None, None)
+
+
+def linear(x, w, b, w_lowp=None):
+    return _Linear.apply(x, w, b, w_lowp, getattr(w, "_gradbuf", None),
+                         getattr(b, "_gradbuf", None) if b is not None else None)
 
 
 def fused_update_local(*a, **k):  # kept for API symmetry; the engine builds FusedPlan objects directly

@@ -60,7 +60,8 @@ for hw, C, K, R, st in shapes:
     if R == 3 and st == 1:
         for v in (1, 3):
             rec(f"halo_fprop_v{v}", lambda i: (lambda: ops.conv3x3_fprop(xs[i], w, stats=False, variant=v)))
-            rec(f"halo_fprop_stats_v{v}", lambda i: (lambda: ops.conv3x3_fprop(xs[i], w, stats=True, variant=v)))
+            # pre-zeroed accumulators, as in the model (bn_apply re-zeroes them): no memset nodes in the timed graph
+            rec(f"halo_fprop_stats_v{v}", lambda i: (lambda: ops.conv3x3_fprop(xs[i], w, stats=(sm, sq), variant=v)))
             rec(f"halo_dgrad_v{v}", lambda i: (lambda: ops.conv3x3_dgrad(dys[i], w, variant=v)))
         rec("halo_wgrad", lambda i: (lambda: ops.conv3x3_wgrad(dys[i], xs[i], out=gb)))
     rows.append(r)

@@ -863,3 +863,135 @@ def test_staging_ring_synthetic():
         seen.append(slot)
     ring.stop()
     assert len(seen) == 5
+
+
+# --------------------------------------------------------------------------- round 2: engine behaviour on the GPU
+def test_set_opt_takes_effect_under_cuda_graph():
+    """Hyper-parameters live in device memory the fused kernel reads at run time, so `set_opt` / LR schedules change
+    the very next replay of an already captured step graph (round-1 ADVICE: they were baked into the graph)."""
+    from fluxdist.parallel.engine import Trainer
+
+    torch.manual_seed(0)
+    tr = Trainer(fd.ResNet18(10), fd.Descent(0.1), fd.CudaDevice(0, 0), 8, image_hw=32, input="u8", graph=True,
+                 backend="native", comm="native")
+    x = torch.randint(0, 256, (8, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    y = torch.randint(0, 10, (8,), device="cuda")
+    tr.capture()
+    w0 = tr.rep.arena.w32.clone()
+    tr.step(x, y)
+    torch.cuda.synchronize()
+    w1 = tr.rep.arena.w32.clone()
+    assert not torch.equal(w0, w1)                      # eta = 0.1: the step moved the weights
+    assert tr.group.comm.step_count(tr.rep) == 1        # capture + warm-up left no trace (state restored)
+    tr.group.set_opt(fd.Descent(0.0))                   # "schedule": learning rate -> 0
+    tr.step(x, y)
+    torch.cuda.synchronize()
+    assert torch.equal(tr.rep.arena.w32, w1)            # the SAME graph now applies eta = 0
+    tr.group.set_opt(fd.Descent(0.05))
+    tr.step(x, y)
+    torch.cuda.synchronize()
+    assert not torch.equal(tr.rep.arena.w32, w1)
+    tr.group.close()
+
+
+def test_staged_loader_overlaps_h2d_with_compute():
+    """The native pinned ring issues the H2D copy of batch i+1 (and i+2) BEFORE batch i's compute is queued, and the
+    copies run on their own stream: N steps of (copy + compute) take about N x compute, not N x (copy + compute)."""
+    from fluxdist.data import StagedLoader
+
+    nbytes = 96 << 20                                   # 96 MB per batch: ~2 ms of PCIe time
+    bank = torch.randint(0, 256, (nbytes,), dtype=torch.uint8)
+    yb = torch.zeros(8, dtype=torch.int64)
+    steps = 12
+    dl = StagedLoader.from_batches(lambda i: (bank, yb), list(range(steps)), "cuda", depth=4, prefetch=2)
+    assert dl.ring is not None, "native PinnedRing not in use"
+    a = torch.randn(4096, 4096, device="cuda", dtype=BF)
+
+    def compute(x):
+        z = a
+        for _ in range(64):  # ~2x the PCIe time of one batch: the copy must hide completely behind it
+            z = (z @ a) * 1e-2
+        return z[0, 0] + x[0].float()
+
+    # reference timings: compute alone, copy alone
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    hx = torch.empty(nbytes, dtype=torch.uint8).pin_memory(); dx = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    compute(dx); dx.copy_(hx, non_blocking=True); torch.cuda.synchronize()
+    e[0].record(); [compute(dx) for _ in range(4)]; e[1].record()
+    e[2].record(); [dx.copy_(hx, non_blocking=True) for _ in range(4)]; e[3].record()
+    torch.cuda.synchronize()
+    t_comp, t_copy = e[0].elapsed_time(e[1]) / 4, e[2].elapsed_time(e[3]) / 4
+    assert 0.25 * t_comp < t_copy < 0.9 * t_comp, (t_copy, t_comp)   # long enough to matter, short enough to hide
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    outs = []
+    for i, (x, y) in enumerate(dl):
+        if i == 2:
+            s0.record()
+        if i >= 1:
+            assert dl.ring.copies_issued() >= min(i + 2, steps)   # next batch's copy already queued
+        outs.append(compute(x))
+    s1.record()
+    torch.cuda.synchronize()
+    per_step = s0.elapsed_time(s1) / (steps - 2)
+    assert per_step < t_comp + 0.35 * t_copy, (per_step, t_comp, t_copy)   # serial would be t_comp + t_copy
+    assert all(torch.isfinite(o) for o in outs)
+
+
+@pytest.mark.parametrize("N,H,W,C,K,R,stride,pad,bias", [(3, 32, 32, 3, 3, 7, 1, 0, True), (2, 13, 17, 5, 7, 3, 2, 1, False),
+                                                         (2, 9, 9, 8, 4, 1, 1, 0, True)])
+def test_direct_conv_small_channels(N, H, W, C, K, R, stride, pad, bias):
+    """Direct (CUDA-core) convolution for channel counts the tcgen05 tiles do not cover: forward, data and weight/bias
+    gradients against fp32 PyTorch (the reference's test model is Conv((7,7),3=>3), test/single_device.jl:117-119)."""
+    from fluxdist.nn.layers import Conv2dN
+
+    torch.manual_seed(0)
+    m = Conv2dN(C, K, R, stride=stride, padding=pad, bias=bias).cuda()
+    ref = copy.deepcopy(m).float()
+    x = torch.randn(N, C, H, W, device="cuda")
+    xa = x.to(BF).requires_grad_(True)
+    xb = x.to(BF).float().requires_grad_(True)
+    n0 = ops.extension().launch_count()
+    fd.nn.set_backend("native")
+    try:
+        ya = m(xa)
+        ya.float().square().mean().backward()
+    finally:
+        fd.nn.set_backend("auto")
+    assert ops.extension().launch_count() - n0 == 3   # fprop, dgrad, wgrad(+bias): all native
+    yb = F.conv2d(xb, ref.weight.to(BF).float(), ref.bias, stride, pad)
+    yb.square().mean().backward(); ref_w_grad = None
+    assert rel_err(ya, yb) < 1e-2
+    assert rel_err(xa.grad, xb.grad) < 2e-2
+    gw = torch.autograd.grad(F.conv2d(xb.detach(), ref.weight, ref.bias, stride, pad).square().mean(), ref.weight)[0]
+    assert rel_err(m.weight.grad, gw) < 3e-2
+    if bias:
+        gb = torch.autograd.grad(F.conv2d(xb.detach(), ref.weight, ref.bias, stride, pad).square().mean(), ref.bias)[0]
+        assert rel_err(m.bias.grad, gb) < 3e-2
+
+
+def test_tiny_convnet_runs_entirely_on_native_kernels():
+    """The reference's test model (Conv((7,7),3=>3) -> flatten -> Dense(2028,10)) through the fused engine: every layer
+    op is one of this repository's kernels (round 1 fell back to cuDNN/cuBLAS) and training tracks the PyTorch path."""
+    from fluxdist.parallel.engine import Trainer
+
+    def run(backend):
+        torch.manual_seed(0)
+        tr = Trainer(fd.tiny_convnet(10), fd.Momentum(0.01, 0.9), fd.CudaDevice(0, 0), 16, image_hw=32, input="float",
+                     graph=False, backend=backend, comm="native")
+        g = torch.Generator().manual_seed(1)
+        x = torch.rand(16, 3, 32, 32, generator=g).cuda()
+        y = torch.randint(0, 10, (16,), generator=g).cuda()
+        n0 = ops.extension().launch_count()
+        ls = [float(tr.step(x, y)) for _ in range(8)]
+        n = ops.extension().launch_count() - n0
+        tr.group.close()
+        return ls, n
+
+    try:
+        ln, launches = run("native")
+        lt, _ = run("torch")
+    finally:
+        fd.nn.set_backend("auto")
+    assert launches >= 8 * 9          # conv fprop/dgrad-free/wgrad, 3 GEMMs + bias + colsum, softmax-CE, fused update per step
+    assert ln[-1] < ln[0]
+    assert all(abs(a - b) < 0.05 * max(abs(b), 0.1) for a, b in zip(ln, lt)), (ln, lt)

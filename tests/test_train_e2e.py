@@ -81,3 +81,84 @@ def test_legacy_argmin_strategy():
     m = run_distributed_argmin(fd.logitcrossentropy, model, lambda i: (x, y), (x, y), fd.fake_devices(2), cycles=1,
                                opt=fd.ADAM(1e-3), batchsize=8, logger=MemoryLogger())
     assert isinstance(m, torch.nn.Module)
+
+
+# --------------------------------------------------------------------------- round 2: resume, collective skip, status
+@pytest.mark.parametrize("engine", ["staged", "fused"])
+def test_checkpoint_resume_restores_optimiser_state_and_shards(engine, tmp_path):
+    """`prepare_training(..., resume=ckpt)`: model weights, optimiser moments + step, shard permutation come back
+    (the reference resumes by passing `sts=` back in, src/sync.jl:101,127-129); a resumed run continues exactly like an
+    uninterrupted one."""
+    mb, _ = _fixed_mb()
+    key = SyntheticKey(400, nclasses=10, shape=(3, 32, 32))
+    opt = fd.ADAM(1e-3)
+    path = str(tmp_path / "ck.pt")
+
+    def run(model, cycle, resume=None, ckpt_every=None):
+        setup, buffer = fd.prepare_training(model, key, fd.fake_devices(2), opt, 8, cycle=cycle, minibatch_fn=mb,
+                                            engine=engine, dtype=torch.float32, seed=3, resume=resume)
+        out = fd.train(fd.logitcrossentropy, setup, buffer, opt, checkpoint_every=ckpt_every, checkpoint_path=path)
+        return setup, out[0][1]
+
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    _, full = run(copy.deepcopy(base), 6)                              # uninterrupted: 6 steps
+    s1, _ = run(copy.deepcopy(base), 3, ckpt_every=3)                  # interrupted after 3 (checkpoint at step 3)
+    ck = torch.load(path, weights_only=False)
+    assert ck["step"] == 3 and len(ck["extra"]["shard_indices"]) == 2
+    s2, resumed = run(fd.tiny_convnet(10), 3, resume=path)             # fresh model object, resumed from the file
+    assert s2.start_step == 3
+    assert all((a == b).all() for a, b in zip(s1.shard_indices, s2.shard_indices))
+    for a, b in zip(resumed.parameters(), full.parameters()):
+        assert torch.allclose(a, b, atol=1e-6), "resumed run diverged from the uninterrupted one"
+
+
+def test_collective_skip_when_one_replica_fails():
+    """A replica that runs out of memory in forward/backward must not leave its peers waiting in the exchange: the
+    batch is skipped on EVERY replica, counted in `Num Missed`, and training goes on in sync (src/ddp_tasks.jl:230-237)."""
+    torch.manual_seed(0)
+    model = fd.tiny_convnet(10)
+    key = SyntheticKey(400, nclasses=10, shape=(3, 32, 32))
+    mb, (x, y) = _fixed_mb()
+    opt = fd.Momentum(1e-3, 0.9)
+    calls = {"n": 0}
+
+    def flaky_loss(out, yy):
+        calls["n"] += 1
+        if calls["n"] == 3:  # second step, first replica to get here
+            raise RuntimeError("CUDA out of memory (injected)")
+        return fd.logitcrossentropy(out, yy)
+
+    setup, buffer = fd.prepare_training(model, key, fd.fake_devices(2), opt, 8, cycle=5, minibatch_fn=mb,
+                                        engine="fused", dtype=torch.float32)
+    steps = []
+    out = fd.train(flaky_loss, setup, buffer, opt, on_step=lambda j, info: steps.append(j))
+    assert len(steps) == 4                      # 5 cycles, one skipped collectively
+    for a, b in zip(out[0][1].parameters(), out[1][1].parameters()):
+        assert torch.equal(a, b)
+    assert setup.engine.ensure_synced()
+
+
+def test_engine_status_check_raises_on_barrier_timeout():
+    """`check_status()` turns the fused kernel's barrier-timeout flag into an exception (round-1: it was write-only)."""
+    from fluxdist.parallel.fused import FusedGroup
+
+    class FakeComm:
+        name = "fake"
+
+        def __init__(self):
+            self.calls = 0
+
+        def status(self, rep):
+            self.calls += 1
+            return (True, self.calls > 1)
+
+        def close(self):
+            pass
+
+    m = fd.tiny_convnet(10)
+    grp = FusedGroup.for_threads([m], fd.fake_devices(1), fd.Momentum(), dtype=torch.float32, comm="thread")
+    grp.comm = FakeComm()
+    assert grp.check_status() == {"nonfinite": True, "barrier_timeout": False}
+    with pytest.raises(RuntimeError, match="barrier timed out"):
+        grp.check_status()
