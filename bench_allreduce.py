@@ -80,12 +80,13 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
 
-    def plan(n, mode, nvls):
+    def plan(n, mode, nvls, unroll=2):
         p = ext.FusedPlan(world, rank, 1, mode, 1 if nvls else 0, n, n, list(hg.buffer_ptrs), w32.data_ptr(),
                           s0.data_ptr(), 0, [], list(hw.buffer_ptrs), list(hf.buffer_ptrs), epoch.data_ptr(),
                           step.data_ptr(), done.data_ptr(), status.data_ptr(), int(hg.multicast_ptr) if nvls else 0, 0,
                           int(hw.multicast_ptr) if nvls else 0, MAX_GRID, local)
         p.set_hyper([0.01, 0.9, 0, 0, 0], 1.0)
+        p.set_unroll(unroll)
         return p
 
     def timed(fn, iters):
@@ -110,8 +111,10 @@ def main():
         n = max(align, (n + align - 1) // align * align)
         G = n * 4
         variants = [("fused/p2p", lambda p=plan(n, MODE_TWO_SHOT, False): p.launch())]
+        variants.append(("fused/p2p/u4", lambda p=plan(n, MODE_TWO_SHOT, False, 4): p.launch()))
         if has_mc:
             variants.append(("fused/nvls", lambda p=plan(n, MODE_TWO_SHOT, True): p.launch()))
+            variants.append(("fused/nvls/u4", lambda p=plan(n, MODE_TWO_SHOT, True, 4): p.launch()))
         if G <= 8 * 1024 * 1024:
             variants.append(("fused/oneshot", lambda p=plan(n, MODE_ONE_SHOT, False): p.launch()))
 

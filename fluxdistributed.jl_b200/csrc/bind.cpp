@@ -3,6 +3,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -43,6 +44,10 @@ struct FusedPlan {
     TORCH_CHECK(n % (4 * world) == 0, "bucket length must be a multiple of 4*world");
     a.world = world; a.rank = rank; a.rule = rule; a.mode = mode; a.use_nvls = use_nvls;
     a.n = n; a.fp32_bcast_from = fp32_bcast_from; a.grad_scale = 1.f;
+    {
+      const char* e = getenv("FLUXDIST_FUSED_UNROLL");
+      a.unroll = (e && atoi(e) >= 4) ? 4 : 2;
+    }
     for (int i = 0; i < FD_MAX_WORLD; ++i) {
       a.g[i] = i < (int)g.size() ? reinterpret_cast<const float*>(g[i]) : nullptr;
       a.wout32[i] = i < (int)wout32.size() ? reinterpret_cast<float*>(wout32[i]) : nullptr;
@@ -69,6 +74,7 @@ struct FusedPlan {
   }
   void set_hyper_dev(int64_t ptr) { a.hyper_dev = reinterpret_cast<const float*>(ptr); }
   void set_step_ptr(int64_t ptr) { a.step_dev = reinterpret_cast<int*>(ptr); }
+  void set_unroll(int u) { a.unroll = u >= 4 ? 4 : 2; }
   void set_max_spins(long long s) { a.max_spins = s; }
   void launch() {
     c10::cuda::CUDAGuard guard(device);
@@ -268,6 +274,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def("set_hyper", &FusedPlan::set_hyper)
       .def("set_hyper_dev", &FusedPlan::set_hyper_dev)
       .def("set_step_ptr", &FusedPlan::set_step_ptr)
+      .def("set_unroll", &FusedPlan::set_unroll)
       .def("set_max_spins", &FusedPlan::set_max_spins)
       .def("launch", &FusedPlan::launch)
       .def_readonly("grid", &FusedPlan::grid);

@@ -27,7 +27,9 @@
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kUnroll = 2;  // float4 per thread per iteration
+// float4 per thread per iteration: 2 (round 1) or 4.  More 16-byte requests in flight per thread cover more of the
+// NVLink / NVSwitch round trip (the in-switch reduction of multimem.ld_reduce has a multi-microsecond latency); picked per
+// plan (FusedArgs::unroll), measured by bench_allreduce.py.
 
 struct Hyper {
   float eta, a, b, eps, decay;
@@ -80,7 +82,7 @@ FD_DEVINL bool cta_barrier(const FusedArgs& A, uint32_t epoch) {
   return true;
 }
 
-template <int RULE, bool NVLS>
+template <int RULE, bool NVLS, int kUnroll = 2>
 __global__ void __launch_bounds__(kThreads) fused_allreduce_update_kernel(const FusedArgs A) {
   const int W = A.world;
   const float inv_w = 1.f / (float)W;
@@ -201,10 +203,17 @@ __global__ void __launch_bounds__(kThreads) fused_allreduce_update_kernel(const 
 
 template <int RULE>
 int launch_rule(const FusedArgs& a, int grid, cudaStream_t s) {
-  if (a.use_nvls)
-    fused_allreduce_update_kernel<RULE, true><<<grid, kThreads, 0, s>>>(a);
-  else
-    fused_allreduce_update_kernel<RULE, false><<<grid, kThreads, 0, s>>>(a);
+  if (a.unroll >= 4) {
+    if (a.use_nvls)
+      fused_allreduce_update_kernel<RULE, true, 4><<<grid, kThreads, 0, s>>>(a);
+    else
+      fused_allreduce_update_kernel<RULE, false, 4><<<grid, kThreads, 0, s>>>(a);
+  } else {
+    if (a.use_nvls)
+      fused_allreduce_update_kernel<RULE, true, 2><<<grid, kThreads, 0, s>>>(a);
+    else
+      fused_allreduce_update_kernel<RULE, false, 2><<<grid, kThreads, 0, s>>>(a);
+  }
   FD_LAUNCH_OK();
   return 0;
 }
@@ -212,6 +221,7 @@ int launch_rule(const FusedArgs& a, int grid, cudaStream_t s) {
 }  // namespace
 
 int fd_fused_update_grid(long n, int world, int mode, int max_grid) {
+  constexpr int kUnroll = 2;
   long n4 = n / 4;
   long slice4 = (mode == FD_MODE_TWO_SHOT && world > 1) ? n4 / world : n4;
   long want = (slice4 + (long)kThreads * kUnroll - 1) / ((long)kThreads * kUnroll);

@@ -10,6 +10,7 @@ enum { FD_MODE_TWO_SHOT = 0, FD_MODE_ONE_SHOT = 1 };
 
 struct FusedArgs {
   int world, rank, rule, mode, use_nvls;
+  int unroll;                           // 16-byte requests per thread per iteration (2 or 4)
   long n;                               // elements in this bucket (multiple of 4*world)
   long fp32_bcast_from;                 // elements >= this offset are also broadcast in fp32
   float grad_scale;                     // extra scale on the mean gradient (loss-scale inverse)

@@ -22,7 +22,7 @@ done
 for envs in ${ENVS:-}; do
   p=$((p+1))
   echo "=== bench native [$envs]"
-  env $(echo $envs | tr ',' ' ') timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $p bench.py --gpus $N --steps ${STEPS:-30} --warmup 5 --no-e2e 2>/dev/null | grep -E '^\{' | tail -1 | python -c "
+  env $(echo $envs | tr ';' ' ') timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $p bench.py --gpus $N --steps ${STEPS:-30} --warmup 5 --no-e2e 2>/dev/null | grep -E '^\{' | tail -1 | python -c "
 import sys,json
 try:
     d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'])
@@ -43,9 +43,10 @@ import json
 rows=[json.loads(l) for l in open("$O/allreduce.jsonl")]
 rows=[r for r in rows if "variant" in r and "bytes" in r]
 sizes=sorted({r["bytes"] for r in rows})
-print("bytes        " + "  ".join(f"{v:>20s}" for v in ["fused/p2p","fused/nvls","fused/oneshot","nccl+opt"]))
+V=["fused/p2p","fused/p2p/u4","fused/nvls","fused/nvls/u4","fused/oneshot","nccl+opt"]
+print("bytes        " + "  ".join(f"{v:>20s}" for v in V))
 for s in sizes:
     d={r["variant"]:r for r in rows if r["bytes"]==s}
-    print(f"{s:12d} " + "  ".join((f"{d[v]['us']:8.1f}us {d[v]['frac_of_roofline']*100:3.0f}%/{(d[v].get('frac_of_900') or 0)*100:3.0f}%" if v in d else " "*20) for v in ["fused/p2p","fused/nvls","fused/oneshot","nccl+opt"]))
+    print(f"{s:12d} " + "  ".join((f"{d[v]['us']:8.1f}us {d[v]['frac_of_roofline']*100:3.0f}%/{(d[v].get('frac_of_900') or 0)*100:3.0f}%" if v in d else " "*20) for v in V))
 PY
 fi
