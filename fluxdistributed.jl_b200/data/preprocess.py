@@ -106,12 +106,33 @@ def weights_dir() -> str:
     return d
 
 
-def getweights(name: str) -> str:
-    """``getweights(name)`` (``preprocess.jl:3-14``): fetch a weight file into the
-    cache.  No network in this environment: only a local hit succeeds."""
+WEIGHTS_URL = os.environ.get("FLUXDIST_WEIGHTS_URL", "")  # base URL of a weight store (http(s):// or file://)
+
+
+def getweights(name: str, url: Optional[str] = None) -> str:
+    """``getweights(name)`` (``preprocess.jl:3-14``): return the cached weight file, downloading it on a miss from
+    ``url`` or ``$FLUXDIST_WEIGHTS_URL/<name>`` (atomic write into the cache).  Without a configured URL or without
+    network access only a local hit succeeds and the error says where to place the file."""
     p = os.path.join(weights_dir(), name)
-    if not os.path.exists(p):
-        raise FileNotFoundError(f"{p} not present and downloading is disabled (no network); place the file there")
+    if os.path.exists(p):
+        return p
+    src = url or (WEIGHTS_URL.rstrip("/") + "/" + name if WEIGHTS_URL else None)
+    if src is None:
+        raise FileNotFoundError(f"{p} not present and no weight store is configured (set FLUXDIST_WEIGHTS_URL or pass "
+                                f"url=); place the file there")
+    import tempfile
+    import urllib.error
+    import urllib.request
+
+    try:
+        with urllib.request.urlopen(src, timeout=60) as r:
+            data = r.read()
+    except (urllib.error.URLError, OSError, ValueError) as e:
+        raise FileNotFoundError(f"could not download {src!r} ({e}); place the file at {p}") from e
+    fd, tmp = tempfile.mkstemp(dir=weights_dir(), prefix=".w-")
+    with os.fdopen(fd, "wb") as f:
+        f.write(data)
+    os.replace(tmp, p)
     return p
 
 

@@ -8,8 +8,10 @@
 * ``Synthetic``   — procedurally generated ImageNet-shaped content (index CSV,
   synset mapping and JPEG blobs are all fabricated on demand); this is what the
   benchmark configs use because the build has no network and no ImageNet.
-* ``S3``-style remote stores (``Data.toml:14-26``) are declared but need
-  network access; opening one raises a clear error.
+* ``S3`` / ``URL`` remote stores (``Data.toml:14-26``): blobs are fetched on demand over HTTP(S) (``file://`` works
+  too, which is how the tests exercise the driver without a network) into a local cache directory and served from
+  there afterwards.  An ``S3`` entry maps to ``https://<bucket>.s3.amazonaws.com/<prefix>/`` unless ``endpoint`` is
+  given.  Without network access the first fetch raises a clear error; cached blobs keep working.
 
 The registry path comes from ``FLUXDIST_DATA_TOML`` or ``Data.toml`` in the CWD /
 repo root, and can be configured in code with :func:`register` — the reference's
@@ -74,6 +76,61 @@ class BlobTree:
 
     def __repr__(self):
         return f"BlobTree({self.root!r})"
+
+
+class RemoteTree:
+    """URL-backed tree with a read-through local cache (reference: DataSets.jl S3 storage driver, ``Data.toml:14-26``).
+
+    ``tree[path]`` downloads ``<base_url>/<path>`` once (atomically, into ``cache_dir``) and reads the cached copy
+    afterwards; ``exists`` checks the cache first, then issues a HEAD / open.  ``timeout`` bounds every request."""
+
+    def __init__(self, base_url: str, cache_dir: Optional[str] = None, timeout: float = 30.0):
+        self.base_url = base_url.rstrip("/")
+        self.cache_dir = cache_dir or os.path.join(os.path.expanduser("~"), ".cache", "fluxdist", "datasets",
+                                                   format(zlib.crc32(self.base_url.encode()), "08x"))
+        self.timeout = timeout
+        os.makedirs(self.cache_dir, exist_ok=True)
+
+    def _local(self, path: str) -> str:
+        return os.path.join(self.cache_dir, path.lstrip("/"))
+
+    def _fetch(self, path: str) -> str:
+        import tempfile
+        import urllib.error
+        import urllib.request
+
+        loc = self._local(path)
+        if os.path.exists(loc):
+            return loc
+        url = f"{self.base_url}/{path.lstrip('/')}"
+        os.makedirs(os.path.dirname(loc) or ".", exist_ok=True)
+        try:
+            with urllib.request.urlopen(url, timeout=self.timeout) as r:
+                data = r.read()
+        except (urllib.error.URLError, OSError, ValueError) as e:
+            raise FileNotFoundError(f"remote dataset blob {url!r} could not be fetched ({e}); no cached copy at {loc!r}") from e
+        fd, tmp = tempfile.mkstemp(dir=os.path.dirname(loc) or ".", prefix=".blob-")
+        with os.fdopen(fd, "wb") as f:
+            f.write(data)
+        os.replace(tmp, loc)  # atomic: concurrent loader threads never see a partial blob
+        return loc
+
+    def exists(self, path: str) -> bool:
+        try:
+            self._fetch(path)
+            return True
+        except FileNotFoundError:
+            return False
+
+    def open(self, path: str, mode: str = "rb"):
+        return open(self._fetch(path), mode)
+
+    def __getitem__(self, path: str) -> bytes:
+        with self.open(path) as f:
+            return f.read()
+
+    def __repr__(self):
+        return f"RemoteTree({self.base_url!r}, cache={self.cache_dir!r})"
 
 
 class SyntheticTree:
@@ -165,7 +222,17 @@ def dataset(name: str):
         if "size" in st:
             kw["size"] = tuple(st["size"])
         return SyntheticTree(**kw)
-    raise RuntimeError(f"dataset {name!r}: storage driver {drv!r} needs network access, unavailable here")
+    if drv in ("S3", "URL", "HTTP"):
+        base = st.get("url") or st.get("endpoint")
+        if base is None and drv == "S3":
+            base = f"https://{st['bucket']}.s3.amazonaws.com"
+        if base is None:
+            raise ValueError(f"dataset {name!r}: the {drv} driver needs `url` (or `bucket` for S3)")
+        if st.get("prefix"):
+            base = base.rstrip("/") + "/" + str(st["prefix"]).strip("/")
+        return RemoteTree(base, cache_dir=os.path.expanduser(st["cache"]) if st.get("cache") else None,
+                          timeout=float(st.get("timeout", 30.0)))
+    raise RuntimeError(f"dataset {name!r}: unknown storage driver {drv!r}")
 
 
 @contextlib.contextmanager

@@ -1,3 +1,5 @@
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -93,8 +95,8 @@ def test_prepare_training_step_count_and_shards():
 def test_registry_lookup():
     tree = D.dataset("imagenet_synthetic")
     assert isinstance(tree, D.SyntheticTree)
-    with pytest.raises(RuntimeError):
-        D.dataset("imagenet")
+    remote = D.dataset("imagenet")  # S3 entry of Data.toml: a URL-backed tree; nothing is fetched until a blob is read
+    assert type(remote).__name__ == "RemoteTree" and "jc-datasets" in remote.base_url
     D.register("tmpds", path="/nonexistent")
     with pytest.raises(FileNotFoundError):
         D.dataset("tmpds")
@@ -114,3 +116,40 @@ def test_dataset_helper_stubs_and_legacy_alias():
     assert len(v) == 6 and D.ground_truth(v, v["ImageId"][0]) == int(v["class_idx"][0])
     assert D.make_fname("ILSVRC2012_val_00000001").endswith("val/ILSVRC2012_val_00000001.JPEG")
     assert len(D.testimgs(tree, 3)) == 3
+
+
+def test_remote_tree_driver_fetches_and_caches(tmp_path):
+    """The remote (S3 / URL) storage driver of the registry (reference Data.toml:14-26): blobs come over a URL once and
+    from the local cache afterwards (file:// stands in for the object store: no network here)."""
+    from fluxdist.data import registry as R
+
+    store = tmp_path / "store" / "imagenet"
+    (store / "sub").mkdir(parents=True)
+    (store / "LOC_synset_mapping.txt").write_text("n01440764 tench\n")
+    (store / "sub" / "blob.bin").write_bytes(b"\x01\x02\x03")
+    R.register("remote_test", driver="S3", endpoint=f"file://{tmp_path / 'store'}", prefix="imagenet",
+               cache=str(tmp_path / "cache"))
+    tree = R.dataset("remote_test")
+    assert isinstance(tree, R.RemoteTree)
+    assert tree["LOC_synset_mapping.txt"] == b"n01440764 tench\n"
+    assert tree.exists("sub/blob.bin") and not tree.exists("missing.bin")
+    (store / "sub" / "blob.bin").unlink()                      # the "network" goes away: the cache still serves it
+    assert tree["sub/blob.bin"] == b"\x01\x02\x03"
+    with pytest.raises(FileNotFoundError):
+        tree["never_there.bin"]
+
+
+def test_getweights_downloads_into_cache(tmp_path, monkeypatch):
+    import torch
+
+    import importlib
+
+    P = importlib.import_module("fluxdist.data.preprocess")
+    src = tmp_path / "srv"
+    src.mkdir()
+    torch.save({"w": torch.arange(3)}, src / "tiny.pt")
+    monkeypatch.setenv("FLUXDIST_WEIGHTS", str(tmp_path / "wcache"))
+    with pytest.raises(FileNotFoundError):
+        P.getweights("tiny.pt")                                  # nothing cached, no store configured
+    p = P.getweights("tiny.pt", url=f"file://{src / 'tiny.pt'}")
+    assert os.path.exists(p) and torch.equal(P.weights("tiny.pt")["w"], torch.arange(3))

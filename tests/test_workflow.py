@@ -62,3 +62,30 @@ def test_workflow_fake_devices(opt):
 @pytest.mark.parametrize("opt", [fd.Momentum(), fd.ADAM()])
 def test_workflow_cuda(opt):
     _run_workflow(_world(3, cuda=True), opt)
+
+
+def test_demo_server_job_picker_and_classify(tmp_path):
+    """The notebook demo's pieces (reference bin/pluto.jl): job picker over saved runs, checkpoint selection, and
+    classification of a raw RGBA canvas frame."""
+    import numpy as np
+    import torch
+
+    import fluxdist as fd
+    from fluxdist.bin.demo_server import DemoState, create_app
+    from fluxdist.utils import save_checkpoint
+
+    root = tmp_path / "weights"
+    m = fd.ResNet18(10)
+    save_checkpoint(str(root / "0" / "resnet18_cycle_20_x.pt"), m, None, step=20)
+    save_checkpoint(str(root / "0" / "resnet18_cycle_40_x.pt"), m, None, step=40)
+    st = DemoState("resnet18", 10, str(root), device="cpu")
+    jobs = st.jobs()
+    assert len(jobs) == 2 and {j["step"] for j in jobs} == {20, 40}
+    assert st.select(jobs[0]["path"]).endswith(".pt")
+    with pytest.raises(ValueError):
+        st.select(str(tmp_path / "elsewhere.pt"))
+    frame = np.random.default_rng(0).integers(0, 255, size=(240, 320, 4), dtype=np.uint8).tobytes()
+    top = st.classify(frame, 320, 240, k=3)
+    assert len(top) == 3 and abs(sum(t["p"] for t in top)) <= 1.0 + 1e-5 and top[0]["p"] >= top[1]["p"]
+    app = create_app(st)                                   # routes exist (served with uvicorn by `main`)
+    assert {"/", "/jobs", "/select", "/classify"} <= {r.path for r in app.routes}
