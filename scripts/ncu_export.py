@@ -1,7 +1,7 @@
 """Turn gpurun_out/ncu_hot.ncu-rep into tracked text evidence (runs on the CPU box: `ncu -i`):
-  profiles/ncu_r2_summary.txt   one block per kernel: duration, cycles, tensor-pipe %, SM/L1/L2/DRAM %, bytes, regs,
+  profiles/r2/ncu_hot_kernels_summary.txt   one block per kernel: duration, cycles, tensor-pipe %, SM/L1/L2/DRAM %, bytes, regs,
                                 occupancy, plus the top stall reasons and hottest SASS lines (source page)
-  profiles/ncu_r2_details.txt   `--page details` of every captured kernel (all sections)"""
+  profiles/r2/ncu_hot_kernels_details.txt   `--page details` of every captured kernel (all sections)"""
 import csv, io, os, subprocess, sys
 rep = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/ncu_hot.ncu-rep"
 labels = []
@@ -41,6 +41,9 @@ while i < len(src_csv):
         blocks.append((name, hi, data)); i = j
     else:
         i += 1
+by_name = {}
+for b in blocks:
+    by_name.setdefault(b[0], b)
 out = ["ncu --set full --clock-control none --import-source on (scripts/ncu_hot.sh -> scripts/ncu_hot.py; B200, second launch of",
        "every kernel, ResNet-34 batch-96 shapes).  Times under the profiler are NOT benchmark numbers.", ""]
 for k, r in enumerate(rows):
@@ -50,8 +53,9 @@ for k, r in enumerate(rows):
     for nm, key in want:
         if key in ix:
             out.append(f"   {nm:26s} {r[ix[key]]:>16s} {units[ix[key]]}")
-    if k < len(blocks):
-        name, hi, data = blocks[k]
+    blk = by_name.pop(r[ix["Kernel Name"]], None)  # the source page holds ONE entry per kernel function: show it once
+    if blk is not None:
+        name, hi, data = blk
         tot = sum(int(d[hi["# Samples"]]) for d in data) or 1
         stall = [h for h in hi if h.startswith("stall_") and "Not Issued" not in h]
         agg = sorted(((sum(int(d[hi[h]]) for d in data), h[6:]) for h in stall), reverse=True)[:6]
@@ -60,6 +64,6 @@ for k, r in enumerate(rows):
             out.append(f"      {int(d[hi['# Samples']]):6d} smp  {d[hi['Source']].strip()[:110]}")
     out.append("")
 os.makedirs("profiles", exist_ok=True)
-open("profiles/ncu_r2_summary.txt", "w").write("\n".join(out))
-open("profiles/ncu_r2_details.txt", "w").write(run("--page", "details"))
+open("profiles/r2/ncu_hot_kernels_summary.txt", "w").write("\n".join(out))
+open("profiles/r2/ncu_hot_kernels_details.txt", "w").write(run("--page", "details"))
 print("\n".join(out[:60]))
