@@ -83,6 +83,8 @@ FD_DEVINL uint32_t ld_acquire_sys(const uint32_t* p) {
 }
 FD_DEVINL void fence_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
 
+FD_DEVINL void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // streaming 128-bit accesses (peer or local)
 FD_DEVINL float4 ld_nc_v4(const float* p) {
   float4 r;

@@ -311,6 +311,19 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int m = quad * 32 + lane;  // accumulator row = 8*g + i  -> pixel (h0+g, w0+i)
       const int h = th * TH + (m >> 3), w = tw * TW + (m & 7);
       const bool valid = (h < P.H) && (w < P.W);
+      // dz epilogue: the BN layer's y (and mask source) rows of this tile are requested BEFORE waiting for the
+      // accumulator, so their global-memory latency overlaps the MMAs instead of serialising with the TMEM reads
+      uint4 ypre[BZ ? NQ * 4 : 1], opre[BZ ? NQ * 4 : 1];
+      if (BZ) {
+        const long off0 = (((long)n * P.H + h) * P.W + w) * P.Nout + n0 + half * NQ * 32;
+#pragma unroll
+        for (int j = 0; j < NQ * 4; ++j) {
+          ypre[j] = valid ? *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_y) + off0 + j * 8)
+                          : make_uint4(0, 0, 0, 0);
+          opre[j] = (valid && P.bz_out) ? *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_out) + off0 + j * 8)
+                                        : make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(&tfull[acc], accph);
       tc_fence_after();
       bf16* orow = reinterpret_cast<bf16*>(P.out) + (((long)n * P.H + h) * P.W + w) * P.Nout + n0;
@@ -345,15 +358,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         float f[32];
         if (BZ) {
           // dz = mask * dx; accumulate sum dz and sum dz*(y - mean) of this lane's column over the CTA's tiles
-          const long off = (((long)n * P.H + h) * P.W + w) * P.Nout + n0 + c0;
           float qv[32];
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
-            uint4 yv = make_uint4(0, 0, 0, 0), ov = yv;
-            if (valid) {
-              yv = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_y) + off + j4 * 8);
-              if (P.bz_out) ov = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(P.bz_out) + off + j4 * 8);
-            }
+            const uint4 yv = ypre[q * 4 + j4], ov = opre[q * 4 + j4];
             const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, ow[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

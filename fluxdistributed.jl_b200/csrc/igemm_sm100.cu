@@ -457,6 +457,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
           const bf16* yrow = reinterpret_cast<const bf16*>(P.bz_y) + (long)row * P.ldo + nt * BN + c_begin;
 #pragma unroll
           for (int j = 0; j < c_count / 8; ++j) ypre[j] = (row < P.M) ? *reinterpret_cast<const uint4*>(yrow + j * 8) : make_uint4(0, 0, 0, 0);
+          // the residual addend and the mask source are read after the accumulator arrives (no registers to spare for
+          // them here): pull their rows into L2 now so those reads do not pay a DRAM round trip per 32-column chunk
+          if (row < P.M) {
+            const long off = (long)row * P.ldo + nt * BN + c_begin;
+            if (P.add) prefetch_l2(reinterpret_cast<const bf16*>(P.add) + off);
+            if (P.bz_out) prefetch_l2(reinterpret_cast<const bf16*>(P.bz_out) + off);
+          }
         }
         if (mi == 0) {
           mbar_wait(&tfull[acc], acc_phase);

@@ -1512,11 +1512,81 @@ int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, i
   FD_LAUNCH_OK();
   return 0;
 }
+// 3x3 / stride-2 / pad-1 max-pool backward, one thread per 2x2 block of input pixels (x 8 channels).  The four pixels
+// (2p+a, 2q+b), a,b in {0,1}, are covered by the windows {p, p+1} x {q, q+1} only — pixel (2p, 2q) by window (p, q)
+// alone, (2p+1, 2q) by (p, q) and (p+1, q), ... — so FOUR window loads (arg-max bytes + gradient) serve four output
+// vectors where the per-pixel kernel issues 1+2+2+4 = 9, and the index arithmetic is paid once per block (the per-pixel
+// kernel was issue-bound: ~390 instructions per output vector, profiles/r2/ncu_hot_kernels_summary.txt [15]).
+// Window-relative position of pixel (2p+a, 2q+b) inside window (p+dp, q+dq): row a+1-2dp, col b+1-2dq.
+__global__ void __launch_bounds__(256)
+maxpool3s2_bwd_block_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N,
+                            int H, int W, int C, int P, int Q) {
+  const int C8 = C / 8;
+  const int HB = (H + 1) / 2, WB = (W + 1) / 2;
+  const long total = (long)N * HB * WB * C8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int cv, qb, pb, n;
+    split4(i, C8, WB, HB, cv, qb, pb, n);
+    uint2 pk[4];
+    V8 dv[4];
+    bool ok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {  // window (pb + dp, qb + dq), u = 2*dp + dq
+      const int p = pb + (u >> 1), q = qb + (u & 1);
+      ok[u] = (p < P) && (q < Q);
+      if (ok[u]) {
+        const long oi = (((long)n * P + p) * Q + q) * C8 + cv;
+        pk[u] = *reinterpret_cast<const uint2*>(idx + oi * 8);
+        dv[u] = ldg8(dout + oi * 8);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int h = 2 * pb + a, w = 2 * qb + b;
+        if (h >= H || w >= W) continue;
+        __nv_bfloat162 acc[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int dp = u >> 1, dq = u & 1;
+          if ((dp == 1 && a == 0) || (dq == 1 && b == 0)) continue;  // even rows/cols belong to one window only
+          if (!ok[u]) continue;
+          const uint32_t pos = (uint32_t)((a + 1 - 2 * dp) * 3 + (b + 1 - 2 * dq));
+          const uint32_t rep = pos * 0x01010101u;
+          const uint32_t m_lo = __vcmpeq4(pk[u].x, rep), m_hi = __vcmpeq4(pk[u].y, rep);
+          const uint32_t w0 = dv[u].u[0] & __byte_perm(m_lo, 0, 0x1100), w1 = dv[u].u[1] & __byte_perm(m_lo, 0, 0x3322);
+          const uint32_t w2 = dv[u].u[2] & __byte_perm(m_hi, 0, 0x1100), w3 = dv[u].u[3] & __byte_perm(m_hi, 0, 0x3322);
+          acc[0] = __hadd2(acc[0], *reinterpret_cast<const __nv_bfloat162*>(&w0));
+          acc[1] = __hadd2(acc[1], *reinterpret_cast<const __nv_bfloat162*>(&w1));
+          acc[2] = __hadd2(acc[2], *reinterpret_cast<const __nv_bfloat162*>(&w2));
+          acc[3] = __hadd2(acc[3], *reinterpret_cast<const __nv_bfloat162*>(&w3));
+        }
+        V8 o;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o.u[e] = *reinterpret_cast<const uint32_t*>(&acc[e]);
+        stg8(dx + ((((long)n * H + h) * W + w) * C8 + cv) * 8, o);
+      }
+    }
+  }
+}
+
 int fd_maxpool_bwd_idx(const void* idx, const void* dout, void* dx, int N, int H, int W, int C, int k, int stride, int pad,
                        cudaStream_t s) {
   const int P = (H + 2 * pad - k) / stride + 1, Q = (W + 2 * pad - k) / stride + 1;
   int grid = grid_for((long)N * H * W * (C / 8), 256, 148 * 16);
-  if (k == 3 && stride == 2 && pad == 1)
+  static int use_block = -1;
+  if (use_block < 0) {
+    const char* e = getenv("FLUXDIST_POOL_BWD_BLOCK");
+    use_block = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (k == 3 && stride == 2 && pad == 1 && use_block) {
+    const int gridb = grid_for((long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), 256, 148 * 16);
+    maxpool3s2_bwd_block_kernel<<<gridb, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(dout),
+                                                      reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q);
+  } else if (k == 3 && stride == 2 && pad == 1)
     maxpool_bwd_idx_kernel<3, 2, 1><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx),
                                                          reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N,
                                                          H, W, C, P, Q, k, stride, pad);
