@@ -446,6 +446,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_cluster_multicast", &fd_set_cluster_multicast);
   m.def("set_epilogue8", &fd_set_epilogue8);
   m.def("set_tile_shape", &fd_set_tile_shape, "force the conv CTA tile shape (bn, m-tiles per CTA); (0, 0) = automatic");
+  m.def("set_pdl", &fd_set_pdl, "bit mask of kernel classes launched with programmatic dependent launch (see common.cuh)");
+  m.def("pdl_mask", &fd_pdl_mask);
   m.def("launch_count", &fd_launch_count, "kernels of this extension launched (or captured) so far");
   fd_bind_staging(m);
 }

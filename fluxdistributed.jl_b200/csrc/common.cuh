@@ -29,6 +29,38 @@ long fd_launch_count();
   } while (0)
 const char* fd_last_error();
 
+// ------------------------------------------------------------------ programmatic dependent launch (PDL)
+// A kernel launched through fd_launch_pdl() may be scheduled while the previous kernel of the stream is still
+// draining: its CTAs run their on-chip prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
+// pdl_wait() until the previous grid has completed and its writes are visible.  Every kernel launched this way MUST
+// execute pdl_wait() before its first global-memory access in every CTA that touches memory (that also keeps the
+// chain transitive: "my predecessor is complete" implies "its predecessor is complete").  pdl_trigger() lets the NEXT
+// kernel of the stream start being scheduled; both are no-ops for a kernel launched without the attribute.
+// The attribute is applied per kernel CLASS (PDL_* below): FLUXDIST_PDL is a bit mask over the classes (0 = plain
+// stream-ordered launches everywhere); fd_set_pdl() overrides it at run time.
+FD_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+FD_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+enum { PDL_IGEMM = 0, PDL_IGEMM_WGRAD = 1, PDL_HALO = 2, PDL_HALO_WGRAD = 3, PDL_BN_FWD = 4, PDL_BN_BWD_FUSED = 5,
+       PDL_BN_BWD_APPLY = 6, PDL_POOL = 7 };
+int fd_pdl_mask();
+void fd_set_pdl(int mask);
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t fd_launch_pdl(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ((fd_pdl_mask() >> cls) & 1) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ packing
 FD_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   bf162 v = __floats2bfloat162_rn(lo, hi);

@@ -147,6 +147,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int nt = blockIdx.x % P.n_tiles;
   const int n0 = nt * BN;
   if (BZ) {
+    pdl_wait();  // the BN parameters are global memory: not before the previous kernel of the stream has completed
     for (int c = threadIdx.x; c < BN; c += blockDim.x) {
       const float mu = P.bz_mean[n0 + c], g = P.bz_gamma[n0 + c] * P.bz_rstd[n0 + c];
       bnpar[c] = mu;
@@ -158,6 +159,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_wait();     // on-chip set-up above overlaps the previous kernel's tail (PDL); global memory only from here on
+  pdl_trigger();
 
   const int m_first = blockIdx.x / P.n_tiles;
   const int m_step = gridDim.x / P.n_tiles;
@@ -499,7 +502,8 @@ int launch_halo(const CUtensorMap& a, const CUtensorMap& b, const HParams& p, cu
   const int total = p.m_tiles * p.n_tiles;
   if (grid > total) grid = total;
   if (grid < p.n_tiles) grid = p.n_tiles;
-  conv_halo_kernel<BN, DGRAD, RESIDENT, STEM, BZ><<<grid, kThreadsConv, smem, s>>>(a, b, p, resident_bytes, a_stages);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_HALO, conv_halo_kernel<BN, DGRAD, RESIDENT, STEM, BZ>, dim3(grid), dim3(kThreadsConv), smem, s, a, b, p,
+                              resident_bytes, a_stages));
   FD_LAUNCH_OK();
   return 0;
 }
@@ -607,6 +611,8 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_wait();     // on-chip set-up above overlaps the previous kernel's tail (PDL); global memory only from here on
+  pdl_trigger();
 
   // work item: (split, group, c-chunk, k-tile)
   int t = blockIdx.x;
@@ -765,6 +771,8 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap mapDY, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  pdl_wait();     // on-chip set-up above overlaps the previous kernel's tail (PDL); global memory only from here on
+  pdl_trigger();
   const int split = blockIdx.x;
   const int mt0 = (int)(((long)P.m_tiles * split) / P.splits);
   const int mt1 = (int)(((long)P.m_tiles * (split + 1)) / P.splits);
@@ -898,7 +906,7 @@ int fd_stem_wgrad(const void* dy, const void* x2, float* dw2, int N, int HS, int
   if (map_s2d_overlap(&mx, x2, N, HS, WS)) return -1;
   const int smem = SW_STAGES * SW_STAGE + 1024 + 256;
   FD_CUDA_CHECK(cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  stem_wgrad_kernel<<<p.splits, kThreads, smem, s>>>(mdy, mx, p);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_HALO_WGRAD, stem_wgrad_kernel, dim3(p.splits), dim3(kThreads), smem, s, mdy, mx, p));
   FD_LAUNCH_OK();
   return 0;
 }
@@ -928,7 +936,7 @@ int fd_conv3x3_wgrad(const void* dy, const void* x, float* dw, int N, int H, int
   if (map_tile4d(&mx, x, N, H, W, C, PW, PH)) return -1;
   const int smem = WG_STAGES * WG_STAGE + 1024 + 256;
   FD_CUDA_CHECK(cudaFuncSetAttribute(wgrad_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  wgrad_halo_kernel<<<base * splits, kThreads, smem, s>>>(mdy, mx, p);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_HALO_WGRAD, wgrad_halo_kernel, dim3(base * splits), dim3(kThreads), smem, s, mdy, mx, p));
   FD_LAUNCH_OK();
   return 0;
 }

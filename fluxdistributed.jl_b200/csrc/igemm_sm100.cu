@@ -210,6 +210,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ C
   if (MC) cluster_sync();  // peers' barriers are initialised before any remote arrive / multicast copy
   tc_fence_after();
   const uint32_t tmem_base = uniform_u32(*tmem_slot);
+  // everything above is on-chip set-up and may overlap the tail of the previous kernel of the stream (PDL); nothing
+  // below touches global memory before the previous grid has completed
+  pdl_wait();
+  pdl_trigger();
   const int crank = MC ? (int)cluster_ctarank() : 0;
 
   // a work unit = MT consecutive m-tiles (MT = 2) or, in cluster mode, a pair of m-tiles split over the two CTAs; an
@@ -695,7 +699,7 @@ int launch(const CUtensorMap& a, const CUtensorMap& b, const KParams& p, cudaStr
   int tiles = ((p.m_tiles + MT - 1) / MT) * p.n_tiles * p.splits;
   int grid = tiles < g_num_sms ? tiles : g_num_sms;
   if (grid < 1) grid = 1;
-  igemm_kernel<BN, MODE, false, BZ, E8, MT><<<grid, C::kThreadsCfg, C::SMEM_BYTES, s>>>(a, b, p);
+  FD_CUDA_CHECK(fd_launch_pdl(MODE == MODE_WGRAD ? PDL_IGEMM_WGRAD : PDL_IGEMM, igemm_kernel<BN, MODE, false, BZ, E8, MT>, dim3(grid), dim3(C::kThreadsCfg), C::SMEM_BYTES, s, a, b, p));
   FD_LAUNCH_OK();
   return 0;
 }

@@ -117,6 +117,8 @@ bn_apply_kernel(const bf16* __restrict__ y, const bf16* __restrict__ res, bf16* 
                 float momentum, int training, int relu, unsigned* consumed) {
   extern __shared__ float smem[];  // scale[C], shift[C]
   __shared__ int s_last;
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   float* sc = smem;
   float* sh = smem + C;
   const float invM = 1.f / (float)M;
@@ -286,6 +288,8 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                     const float* __restrict__ beta, const float* __restrict__ dgamma, const float* __restrict__ dbeta,
                     bf16* __restrict__ dy, bf16* __restrict__ dres, long M, int C, int relu) {
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   extern __shared__ float smem[];  // a[C], b[C], c[C], sc[C], sh[C]:  dy = a*dz + b*y + c ; pre-act = sc*y + sh
   float* ka = smem;
   float* kb = smem + C;
@@ -500,6 +504,8 @@ bn_bwd_fused_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y, c
   constexpr int U = 4;
   extern __shared__ float smem[];
   __shared__ unsigned s_gen0;
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   const int C8 = C / 8;
   const int RL = 256 / C8;
   const int cv = threadIdx.x % C8, rl = threadIdx.x / C8;
@@ -783,6 +789,8 @@ bn_bwd_apply_kernel(const bf16* __restrict__ dz, const bf16* __restrict__ y, con
                     const float* __restrict__ rstd, const float* __restrict__ gamma, float* s0, float* s1,
                     float* __restrict__ dgamma, float* __restrict__ dbeta, bf16* __restrict__ dy, long M, int C,
                     unsigned* consumed) {
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   extern __shared__ float smem[];
   __shared__ int s_last;
   float* ka = smem;
@@ -870,6 +878,8 @@ bn_relu_pool3s2_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, uint8
                        int training, unsigned* consumed) {
   extern __shared__ float smem[];  // scale[C], shift[C]
   __shared__ int s_last;
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   float* sc = smem;
   float* sh = smem + C;
   const long M = (long)N * H * W;
@@ -1440,9 +1450,10 @@ int fd_bn_apply(const void* y, const void* res, void* out, float* sum, float* su
                 const float* beta, float* run_mean, float* run_var, float* save_mean, float* save_rstd, long M, int C,
                 float eps, float momentum, int training, int relu, unsigned* consumed, cudaStream_t s) {
   int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
-  bn_apply_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
-      reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res), reinterpret_cast<bf16*>(out), sum, sumsq,
-      gamma, beta, run_mean, run_var, save_mean, save_rstd, M, C, eps, momentum, training, relu, consumed);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_BN_FWD, bn_apply_kernel, dim3(grid), dim3(256), 2 * C * sizeof(float), s,
+                              reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(res),
+                              reinterpret_cast<bf16*>(out), sum, sumsq, gamma, beta, run_mean, run_var, save_mean, save_rstd,
+                              M, C, eps, momentum, training, relu, consumed));
   FD_LAUNCH_OK();
   return 0;
 }
@@ -1472,9 +1483,11 @@ int fd_bn_bwd_apply(const void* dz, const void* y, const float* mean, const floa
                     float* s1, float* dgamma, float* dbeta, void* dy, long M, int C, unsigned* consumed, cudaStream_t s) {
   if (C % 8) { fd_set_error("bn_bwd_apply: C must be a multiple of 8", __FILE__, __LINE__); return -1; }
   int grid = grid_for(M * (C / 8), 256 * 4, 148 * 8);
-  bn_bwd_apply_kernel<<<grid, 256, 3 * C * sizeof(float), s>>>(
-      reinterpret_cast<const bf16*>(dz), reinterpret_cast<const bf16*>(y), mean, rstd, gamma, s0, s1, dgamma, dbeta,
-      reinterpret_cast<bf16*>(dy), M, C, consumed);
+  void (*kern)(const bf16*, const bf16*, const float*, const float*, const float*, float*, float*, float*, float*, bf16*,
+               long, int, unsigned*) = bn_bwd_apply_kernel;  // the dz overload
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_BN_BWD_APPLY, kern, dim3(grid), dim3(256), 3 * C * sizeof(float), s, reinterpret_cast<const bf16*>(dz),
+                              reinterpret_cast<const bf16*>(y), mean, rstd, gamma, s0, s1, dgamma, dbeta,
+                              reinterpret_cast<bf16*>(dy), M, C, consumed));
   FD_LAUNCH_OK();
   return 0;
 }
@@ -1485,9 +1498,10 @@ int fd_bn_relu_pool(const void* y, void* out, void* idx, float* sum, float* sums
   if (C % 8) { fd_set_error("bn_relu_pool: C must be a multiple of 8", __FILE__, __LINE__); return -1; }
   const int P = (H + 2 - 3) / 2 + 1, Q = (W + 2 - 3) / 2 + 1;
   int grid = grid_for((long)N * P * Q * (C / 8), 256, 148 * 8);
-  bn_relu_pool3s2_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(
-      reinterpret_cast<const bf16*>(y), reinterpret_cast<bf16*>(out), reinterpret_cast<uint8_t*>(idx), sum, sumsq, gamma,
-      beta, run_mean, run_var, save_mean, save_rstd, N, H, W, C, P, Q, eps, momentum, training, consumed);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_BN_FWD, bn_relu_pool3s2_kernel, dim3(grid), dim3(256), 2 * C * sizeof(float), s,
+                              reinterpret_cast<const bf16*>(y), reinterpret_cast<bf16*>(out),
+                              reinterpret_cast<uint8_t*>(idx), sum, sumsq, gamma, beta, run_mean, run_var, save_mean,
+                              save_rstd, N, H, W, C, P, Q, eps, momentum, training, consumed));
   FD_LAUNCH_OK();
   return 0;
 }
@@ -1521,6 +1535,8 @@ int fd_maxpool_bwd(const void* x, const void* out, const void* dout, void* dx, i
 __global__ void __launch_bounds__(256)
 maxpool3s2_bwd_block_kernel(const uint8_t* __restrict__ idx, const bf16* __restrict__ dout, bf16* __restrict__ dx, int N,
                             int H, int W, int C, int P, int Q) {
+  pdl_wait();  // PDL: scheduled early, global memory only once the previous kernel of the stream has completed
+  pdl_trigger();
   const int C8 = C / 8;
   const int HB = (H + 1) / 2, WB = (W + 1) / 2;
   const long total = (long)N * HB * WB * C8;
@@ -1584,8 +1600,9 @@ int fd_maxpool_bwd_idx(const void* idx, const void* dout, void* dx, int N, int H
   }
   if (k == 3 && stride == 2 && pad == 1 && use_block) {
     const int gridb = grid_for((long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8), 256, 148 * 16);
-    maxpool3s2_bwd_block_kernel<<<gridb, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(dout),
-                                                      reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q);
+    FD_CUDA_CHECK(fd_launch_pdl(PDL_POOL, maxpool3s2_bwd_block_kernel, dim3(gridb), dim3(256), 0, s,
+                                reinterpret_cast<const uint8_t*>(idx), reinterpret_cast<const bf16*>(dout),
+                                reinterpret_cast<bf16*>(dx), N, H, W, C, P, Q));
   } else if (k == 3 && stride == 2 && pad == 1)
     maxpool_bwd_idx_kernel<3, 2, 1><<<grid, 256, 0, s>>>(reinterpret_cast<const uint8_t*>(idx),
                                                          reinterpret_cast<const bf16*>(dout), reinterpret_cast<bf16*>(dx), N,
@@ -1754,9 +1771,10 @@ int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const floa
   if (grid < 1) { fd_set_error("bn_bwd_fused: occupancy query failed", __FILE__, __LINE__); return -1; }
   GridSync gs{reinterpret_cast<unsigned*>(ws), reinterpret_cast<unsigned*>(ws) + 1};
   float* accbuf = reinterpret_cast<float*>(ws) + 4;
-  bn_bwd_fused_kernel<<<grid, 256, smem, s>>>(
-      reinterpret_cast<const bf16*>(dout), reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean,
-      rstd, gamma, beta, dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), accbuf, gs, M, C, relu);
+  FD_CUDA_CHECK(fd_launch_pdl(PDL_BN_BWD_FUSED, bn_bwd_fused_kernel, dim3(grid), dim3(256), smem, s, reinterpret_cast<const bf16*>(dout),
+                              reinterpret_cast<const bf16*>(y), reinterpret_cast<const bf16*>(out), mean, rstd, gamma, beta,
+                              dgamma, dbeta, reinterpret_cast<bf16*>(dy), reinterpret_cast<bf16*>(dres), accbuf, gs, M, C,
+                              relu));
   FD_LAUNCH_OK();
   return 0;
 }

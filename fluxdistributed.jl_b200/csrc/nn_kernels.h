@@ -61,3 +61,7 @@ int fd_bn_bwd_pool_fused(const void* idx, const void* g, const void* y, const fl
 int fd_bn_bwd_fused(const void* dout, const void* y, const void* out, const float* mean, const float* rstd,
                     const float* gamma, const float* beta, float* dgamma, float* dbeta, void* dy, void* dres, void* ws,
                     long M, int C, int relu, cudaStream_t s);
+
+// programmatic dependent launch switch (error.cu)
+int fd_pdl_mask();
+void fd_set_pdl(int mask);

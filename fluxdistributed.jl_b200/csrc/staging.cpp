@@ -10,7 +10,11 @@
 //       2. top up the copies in flight (up to `prefetch` slots ahead): cudaStreamWaitEvent(copy, consumed[s]) ->
 //          cudaMemcpyAsync(H2D) of x and y on the copy stream -> record `copied[s]`;
 //       3. hand out the oldest copy in flight: the compute stream waits on `copied[s]`.
-// The H2D copy of step i+1 (and i+2) is therefore issued before step i's compute is even queued and overlaps it.
+// Copies are ALSO issued from commit() (the producer's thread) whenever fewer than `prefetch` are in flight, so a
+// batch that becomes ready while the consumer is busy queueing step i starts its transfer immediately instead of at
+// the next next() call.  The H2D copy of step i+1 (and i+2) therefore overlaps step i's compute whichever side is
+// ahead.  All queue state (free / ready / in flight) is guarded by one mutex; the CUDA calls made under it are
+// asynchronous enqueues.
 #include <cuda_runtime.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -82,9 +86,9 @@ class PinnedRing {
   uintptr_t host_x(int s) const { return (uintptr_t)hx_[s]; }
   uintptr_t host_y(int s) const { return (uintptr_t)hy_[s]; }
   void commit(int s) {
-    std::lock_guard<std::mutex> lk(mu_);
-    ready_.push_back(s);
-    cv_.notify_all();
+    py::gil_scoped_release nogil;
+    RT_CHECK(cudaSetDevice(device_));
+    commit_slot(s);
   }
 
   // ---- built-in synthetic producer (uint8 NHWC pixels, int64 labels)
@@ -98,6 +102,7 @@ class PinnedRing {
       b = (uint8_t)(s >> 32);
     }
     worker_ = std::thread([this, steps, batch, nclasses, seed] {
+      cudaSetDevice(device_);
       uint64_t st = seed + 12345;
       const size_t img = xb_ / batch;
       for (long it = 0; it < steps && !stopping_; ++it) {
@@ -117,7 +122,14 @@ class PinnedRing {
           std::memcpy(x + (size_t)b * img, bank_.data() + off, img);
           if (yb_) y[b] = (long long)((st >> 20) % (uint64_t)nclasses);
         }
-        commit(slot);
+        try {
+          commit_slot(slot);
+        } catch (const std::exception&) {  // a failed enqueue ends the stream of batches; next() reports "stopped"
+          std::lock_guard<std::mutex> lk(mu_);
+          stopping_ = true;
+          cv_.notify_all();
+          return;
+        }
       }
     });
   }
@@ -136,13 +148,21 @@ class PinnedRing {
       last_ = -1;
       cv_.notify_all();
     }
-    top_up(false);
-    if (inflight_.empty()) top_up(true);  // nothing ready yet: block for the producer
-    const int s = inflight_.front();
-    inflight_.pop_front();
+    int s;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      issue_ready_locked();
+      if (inflight_.empty()) {  // nothing ready yet: block for the producer (its commit() issues the copy)
+        cv_.wait(lk, [&] { return !inflight_.empty() || !ready_.empty() || stopping_; });
+        issue_ready_locked();
+        if (inflight_.empty()) throw std::runtime_error("staging ring stopped");
+      }
+      s = inflight_.front();
+      inflight_.pop_front();
+      last_ = s;
+      issue_ready_locked();  // the copy of the NEXT batch is queued before this batch's compute
+    }
     RT_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, copied_[s], 0));
-    last_ = s;
-    top_up(false);  // the copy of the NEXT batch is queued before this batch's compute
     const uintptr_t px = (uintptr_t)dx_[s], py_ = (uintptr_t)dy_[s];
     py::gil_scoped_acquire gil;
     return py::make_tuple(s, px, py_);
@@ -150,7 +170,7 @@ class PinnedRing {
 
   // wall-clock independent evidence of overlap for tests: copies issued so far, and copies that had ALREADY been
   // issued when their batch was handed out one step earlier (= prefetched ahead of the compute that precedes them)
-  long copies_issued() const { return issued_; }
+  long copies_issued() const { return issued_.load(); }
 
   void stop() {
     {
@@ -165,28 +185,24 @@ class PinnedRing {
   int depth() const { return depth_; }
 
  private:
-  // issue H2D copies for ready slots until `prefetch_` are in flight; block == true waits for one ready slot
-  void top_up(bool block) {
-    for (;;) {
-      int s = -1;
-      {
-        std::unique_lock<std::mutex> lk(mu_);
-        if ((int)inflight_.size() >= prefetch_) return;
-        if (block) cv_.wait(lk, [&] { return !ready_.empty() || stopping_; });
-        if (ready_.empty()) {
-          if (block) throw std::runtime_error("staging ring stopped");
-          return;
-        }
-        s = ready_.front();
-        ready_.pop_front();
-      }
+  void commit_slot(int s) {
+    std::lock_guard<std::mutex> lk(mu_);
+    ready_.push_back(s);
+    issue_ready_locked();
+    cv_.notify_all();
+  }
+
+  // issue H2D copies for ready slots (FIFO) until `prefetch_` are in flight; mu_ held, current device = device_
+  void issue_ready_locked() {
+    while ((int)inflight_.size() < prefetch_ && !ready_.empty()) {
+      const int s = ready_.front();
+      ready_.pop_front();
       RT_CHECK(cudaStreamWaitEvent(copy_, consumed_[s], 0));  // device buffers of slot s no longer read by compute
       RT_CHECK(cudaMemcpyAsync(dx_[s], hx_[s], xb_, cudaMemcpyHostToDevice, copy_));
       if (yb_) RT_CHECK(cudaMemcpyAsync(dy_[s], hy_[s], yb_, cudaMemcpyHostToDevice, copy_));
       RT_CHECK(cudaEventRecord(copied_[s], copy_));
       inflight_.push_back(s);
       ++issued_;
-      block = false;
     }
   }
 
@@ -194,8 +210,8 @@ class PinnedRing {
   size_t xb_, yb_;
   int depth_;
   int prefetch_;
-  std::deque<int> inflight_;  // consumer thread only
-  long issued_ = 0;
+  std::deque<int> inflight_;  // guarded by mu_ (producer and consumer both issue copies)
+  std::atomic<long> issued_{0};
   cudaStream_t copy_{};
   std::vector<void*> hx_, hy_, dx_, dy_;
   std::vector<cudaEvent_t> copied_, consumed_;

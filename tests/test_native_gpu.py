@@ -3,6 +3,7 @@ same op.  All tests need a GPU and the in-tree extension —
 (not skip) if the extension cannot be loaded on a CUDA box."""
 import copy
 import os
+import time
 
 import pytest
 import torch
@@ -932,7 +933,12 @@ def test_staged_loader_overlaps_h2d_with_compute():
         if i == 2:
             s0.record()
         if i >= 1:
-            assert dl.ring.copies_issued() >= min(i + 2, steps)   # next batch's copy already queued
+            # the NEXT batch's copy gets queued without another next() call (commit() issues it as soon as the producer
+            # has filled the slot); the producer runs on its own thread, so allow it a bounded time
+            t_end = time.time() + 5.0
+            while dl.ring.copies_issued() < min(i + 2, steps) and time.time() < t_end:
+                time.sleep(0.0005)
+            assert dl.ring.copies_issued() >= min(i + 2, steps)
         outs.append(compute(x))
     s1.record()
     torch.cuda.synchronize()
