@@ -14,7 +14,7 @@ so = glob.glob(os.path.join(ROOT, "fluxdistributed.jl_b200", "_C.*.so"))[0]
 out_dir = os.path.join(ROOT, "profiles", "sass")
 os.makedirs(out_dir, exist_ok=True)
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UTMAREDG|LDTM|STTM|UTCBAR|UBLKCP|LDGMC|STGMC|REDG|UTCATOMSWS|UCGABAR|SYNCS)")
+KEY = re.compile(r"\b(UTCHMMA|UTCQMMA|UTMALDG|UTMASTG|UTMAREDG|LDTM|STTM|UTCBAR|UBLKCP|LDGMC|STGMC|REDG|UTCATOMSWS|UCGABAR|SYNCS|ACQBULK|PREEXIT)")
 WINDOW = 12
 funcs = re.split(r"\n\s*Function : ", txt)[1:]
 counts = {}
@@ -66,7 +66,8 @@ for f in funcs:
 with open(os.path.join(ROOT, "profiles", "sass_mnemonics_r2.txt"), "w") as fh:
     fh.write("Per-kernel counts of Blackwell-specific SASS mnemonics (scripts/dump_sass.py; listings in profiles/sass/).\n"
              "UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTMALDG = TMA load (tiled / IM2COL / MULTICAST),\n"
-             "LDGMC/STGMC = multimem.ld_reduce / multimem.st, REDG = red.global (vector fp32 atomics), SYNCS = mbarrier ops.\n\n")
+             "LDGMC/STGMC = multimem.ld_reduce / multimem.st, REDG = red.global (vector fp32 atomics), SYNCS = mbarrier ops,\n"
+             "ACQBULK / PREEXIT = griddepcontrol.wait / griddepcontrol.launch_dependents (programmatic dependent launch).\n\n")
     for sn, n, k in sorted(index):
         c = counts[sn]
         if not c:
