@@ -579,6 +579,15 @@ class FusedGroup:
                 pass
         return len(set(sums)) == 1
 
+    def verify_exchange(self, rounds: int = 2, raise_on_error: bool = True) -> Dict[str, Any]:
+        """Debug mode of the gradient exchange: poison every bucket with a known per-rank pattern and the
+        kernel's outputs with NaN, run the real ``reduce_and_update``, check every parameter element against the
+        optimiser rule applied to the known mean and (native path) the barrier epochs / step counters / status words;
+        state is restored afterwards.  Collective in process mode.  See ``parallel/debug.py``."""
+        from .debug import verify_exchange as _verify
+
+        return _verify(self, rounds=rounds, raise_on_error=raise_on_error)
+
     def close(self) -> None:
         self.comm.close()
 

@@ -181,6 +181,10 @@ def _worker_loop(rank: int, nworkers: int, loss, tree, m: nn.Module, key, c, op,
                 # resume: moments and step counter go into the arena (the logical state the reference passes as `sts=`,
                 # src/sync.jl:101,127-129); ADVICE r1: the fused transport used to ignore it
                 rep.load_state_tree(st)
+            if os.environ.get("FLUXDIST_DEBUG_EXCHANGE", "0") == "1":
+                # debug mode: every worker poisons its buckets and checks the exchange (collective)
+                vr = engine.verify_exchange()
+                lg.info("verify_exchange", **{k: v for k, v in vr.items() if k != "errors"})
             graphed = dev.is_cuda and engine.comm.name == "native" if use_graph is None else bool(use_graph)
             # the channels carry one token per step (step id, NaN flag): posted from a helper thread so the gradient
             # server stays informed without the training loop ever waiting for a host round trip

@@ -27,6 +27,7 @@ from __future__ import annotations
 
 import copy
 import math
+import os
 from concurrent.futures import Future, ThreadPoolExecutor
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple
@@ -207,6 +208,10 @@ def prepare_training(model: nn.Module, key, devices: Sequence, opt: Rule, nsampl
             for r in setup.engine.replicas:  # moments + step counter into the arenas (sharded masters included)
                 with device_ctx(r.dev):
                     r.load_state_tree(sts[r.dev], step_count=setup.start_step)
+        if os.environ.get("FLUXDIST_DEBUG_EXCHANGE", "0") == "1":
+            # debug mode: poisoned-bucket self test of the gradient exchange before the first step
+            rep_ = setup.engine.verify_exchange()
+            get_logger().info("verify_exchange", **{k: v for k, v in rep_.items() if k != "errors"})
     return setup, buffer
 
 

@@ -1,4 +1,5 @@
 #!/bin/bash
+# NOTE: FLUXDIST_PDL_LATE existed only for this experiment (results: profiles/r2/pdl_ab.txt, run 3); the switch was removed afterwards.
 # third PDL A/B: conv kernels release their dependents late (FLUXDIST_PDL_LATE=1) so BN kernels can be dependents
 set -u
 O=gpurun_out/r2pdl3; mkdir -p $O

@@ -150,3 +150,90 @@ def test_fused_group_resume_from_state_trees(opt):
     for a, b in zip(second.replicas[0].model.parameters(), full.replicas[0].model.parameters()):
         assert torch.allclose(a, b, atol=1e-6)
     assert compare(second.state_trees()[devs[0]], full.state_trees()[devs[0]], 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("opt", [fd.Momentum(0.05, 0.9), fd.ADAM(1e-2), fd.Nesterov(0.05, 0.9), fd.Descent(0.1)])
+def test_verify_exchange_passes_and_is_side_effect_free(opt):
+    """Debug mode of the gradient exchange: poisoned buckets in, rule(mean) out on every replica, state
+    untouched afterwards."""
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    n = 3
+    grp = FusedGroup.for_threads([copy.deepcopy(base) for _ in range(n)], fd.fake_devices(n), opt, dtype=torch.float32)
+    x, y = _batches(n)
+    with ThreadPoolExecutor(n) as ex:  # one real step first so moments / step counters are non-trivial
+        [f.result() for f in [ex.submit(grp.replicas[i].step, x[3 * i:3 * i + 3], y[3 * i:3 * i + 3],
+                                        fd.logitcrossentropy) for i in range(n)]]
+    before = [(r.arena.w32.clone(), [s.clone() for s in r.arena.slots], r.step_count) for r in grp.replicas]
+    rep = grp.verify_exchange(rounds=2)
+    assert rep["ok"] and rep["replicas"] == n and rep["checked_elems"] > 0 and rep["max_rel_err"] < 1e-4
+    for r, (w, sl, sc) in zip(grp.replicas, before):
+        assert torch.equal(r.arena.w32, w) and r.step_count == sc
+        assert all(torch.equal(a, b) for a, b in zip(r.arena.slots, sl))
+        assert float(r.arena.g32.abs().sum()) == 0.0
+    with ThreadPoolExecutor(n) as ex:  # and training continues
+        [f.result() for f in [ex.submit(grp.replicas[i].step, x[3 * i:3 * i + 3], y[3 * i:3 * i + 3],
+                                        fd.logitcrossentropy) for i in range(n)]]
+    assert grp.ensure_synced()
+
+
+def test_verify_exchange_catches_a_broken_exchange():
+    """Fault injection: a communicator that forgets one replica's contribution on part of the arena, and one that skips
+    the update of a slice, are both reported."""
+    from fluxdist.parallel.debug import ExchangeError
+    from fluxdist.parallel.fused import ThreadComm
+
+    torch.manual_seed(0)
+    base = fd.tiny_convnet(10)
+    n = 2
+    grp = FusedGroup.for_threads([copy.deepcopy(base) for _ in range(n)], fd.fake_devices(n), fd.Momentum(),
+                                 dtype=torch.float32)
+    assert grp.verify_exchange()["ok"]
+    good = ThreadComm.allreduce_update
+
+    def drops_a_rank(self, rep):  # rank 1's gradient of the first 100 elements never arrives
+        keep = self.replicas[1].arena.g32[:100].clone()
+        if rep.rank == 0:
+            self.replicas[1].arena.g32[:100] = self.replicas[0].arena.g32[:100]
+        good(self, rep)
+        if rep.rank == 0:
+            self.replicas[1].arena.g32[:100] = keep
+
+    def skips_a_slice(self, rep):
+        good(self, rep)
+        if rep.rank == 1:
+            rep.arena.w32[200:300] = float("nan")  # as if nobody had broadcast this slice to replica 1
+
+    for broken, needle in ((skips_a_slice, "never written"), (drops_a_rank, "differs")):
+        ThreadComm.allreduce_update = broken
+        try:
+            with pytest.raises(ExchangeError, match=needle):
+                grp.verify_exchange()
+            rep = grp.verify_exchange(raise_on_error=False)
+            assert not rep["ok"] and rep["errors"]
+        finally:
+            ThreadComm.allreduce_update = good
+    assert grp.verify_exchange()["ok"]
+
+
+def _gloo_verify_worker(rank, world, port, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(10)
+    grp = FusedGroup.for_process(fd.tiny_convnet(10), fd.FakeDevice(rank), fd.ADAM(1e-2), dtype=torch.float32, comm="dist")
+    rep = grp.verify_exchange()
+    q.put((rank, rep["ok"], rep["checked_elems"], rep["max_rel_err"]))
+    dist.destroy_process_group()
+
+
+def test_verify_exchange_gloo_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_gloo_verify_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in ps]
+    res = [q.get(timeout=120) for _ in range(world)]
+    [p.join(30) for p in ps]
+    assert all(ok and n > 0 and err < 1e-4 for _, ok, n, err in res), res

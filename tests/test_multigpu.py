@@ -45,6 +45,8 @@ def test_thread_mode_real_gpus(mode, opt):
                                  dtype=torch.float32, comm="native", mode=mode)
     for r in grp.replicas:
         grp.comm.set_max_spins(r, 1 << 23)
+    vr = grp.verify_exchange()  # poisoned-bucket debug mode on the production kernel; side-effect free (checked below)
+    assert vr["ok"] and vr["checked_elems"] > 0, vr
     x, y = _batches(n)
     per = x.shape[0] // n
     with ThreadPoolExecutor(n) as ex:
@@ -88,6 +90,7 @@ def _proc(rank, world, port, nvls, mode, q):
     grp = FusedGroup.for_process(m, fd.CudaDevice(rank, rank), opt, dtype=torch.float32, comm="native", mode=mode)
     rep = grp.replicas[0]
     grp.comm.set_max_spins(rep, 1 << 23)
+    vr = grp.verify_exchange(raise_on_error=False)  # collective; must leave no trace (the reference comparison below)
     x, y = _batches(world)
     per = x.shape[0] // world
     for _ in range(3):
@@ -95,7 +98,7 @@ def _proc(rank, world, port, nvls, mode, q):
     torch.cuda.synchronize()
     st = grp.comm.status(rep)
     grp.sync_to_modules()
-    q.put((rank, [p.detach().cpu().clone() for p in m.parameters()], st, rep.comm_info))
+    q.put((rank, [p.detach().cpu().clone() for p in m.parameters()], st, rep.comm_info, vr))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -120,6 +123,7 @@ def test_process_mode_symmetric_memory(nvls, mode):
     print("comm_info", res[0][3])
     for r in range(world):
         assert res[r][2] == (False, False)
+        assert res[r][4]["ok"] and res[r][4]["checked_elems"] > 0, res[r][4]
         for a, b, c in zip(res[r][1], res[0][1], ref.parameters()):
             assert torch.equal(a, b)
             assert torch.allclose(a, c, rtol=1e-3, atol=2e-4)
@@ -193,3 +197,24 @@ def test_start_fused_transport(use_graph):
         assert torch.allclose(a, b, rtol=5e-2, atol=5e-3)  # bf16 autocast vs the fp32 single-device run
     # optimiser state came back in the reference's logical tree form
     assert fd.compare(res[0][1], res[-1][1], 0.0, 0.0) if hasattr(fd, "compare") else True
+
+
+def test_verify_exchange_bf16_resnet_thread_mode():
+    """Debug mode on the benchmark configuration's data path: ResNet-18 arenas with bf16 compute weights (bf16 broadcast
+    for conv / FC weights, fp32 broadcast for the BN tail, sharded fp32 masters), task mode on real GPUs."""
+    from fluxdist.parallel import FusedGroup
+
+    n = min(torch.cuda.device_count(), 4)
+    torch.manual_seed(0)
+    base = fd.ResNet18(10)
+    devs = fd.cuda_devices(n)
+    for opt in (fd.Momentum(0.01, 0.9), fd.ADAM(1e-3)):
+        grp = FusedGroup.for_threads([copy.deepcopy(base).to(d.torch_device).to(memory_format=torch.channels_last)
+                                      for d in devs], devs, opt, comm="native")
+        assert grp.replicas[0].arena.w16 is not None
+        w0 = [r.arena.w16.clone() for r in grp.replicas]
+        vr = grp.verify_exchange(rounds=3)
+        assert vr["ok"] and vr["comm"] == "native" and vr["checked_elems"] >= 3 * n * 11_000_000, vr
+        assert all(v > 0 for v in vr["epoch_advance_per_bucket"].values())
+        assert all(torch.equal(a, r.arena.w16) for a, r in zip(w0, grp.replicas))
+        grp.close()

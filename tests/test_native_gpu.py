@@ -899,6 +899,32 @@ def test_set_opt_takes_effect_under_cuda_graph():
     tr.group.close()
 
 
+@pytest.mark.parametrize("opt", [fd.Momentum(0.01, 0.9), fd.ADAM(1e-3), fd.Nesterov(0.01, 0.9)])
+def test_verify_exchange_single_gpu_native(opt):
+    """Debug mode of the fused update kernel at world size 1: poisoned gradient arena in, rule(gradient) out
+    in both the fp32 masters and the bf16 compute weights, step counter +1, status clean; the captured step graph keeps
+    working afterwards and training state is untouched."""
+    from fluxdist.parallel.engine import Trainer
+
+    torch.manual_seed(0)
+    tr = Trainer(fd.ResNet18(10), opt, fd.CudaDevice(0, 0), 8, image_hw=32, input="u8", graph=True, backend="native",
+                 comm="native")
+    x = torch.randint(0, 256, (8, 32, 32, 3), dtype=torch.uint8, device="cuda")
+    y = torch.randint(0, 10, (8,), device="cuda")
+    tr.capture()
+    tr.step(x, y)
+    torch.cuda.synchronize()
+    w1, s1 = tr.rep.arena.w32.clone(), [s.clone() for s in tr.rep.arena.slots]
+    vr = tr.group.verify_exchange(rounds=2)
+    assert vr["ok"] and vr["comm"] == "native" and vr["checked_elems"] > 2 * 11_000_000, vr
+    assert torch.equal(tr.rep.arena.w32, w1) and all(torch.equal(a, b) for a, b in zip(tr.rep.arena.slots, s1))
+    assert tr.group.comm.step_count(tr.rep) == 1
+    tr.step(x, y)
+    torch.cuda.synchronize()
+    assert tr.group.comm.step_count(tr.rep) == 2 and not torch.equal(tr.rep.arena.w32, w1)
+    tr.group.close()
+
+
 def test_staged_loader_overlaps_h2d_with_compute():
     """The native pinned ring issues the H2D copy of batch i+1 (and i+2) BEFORE batch i's compute is queued, and the
     copies run on their own stream: N steps of (copy + compute) take about N x compute, not N x (copy + compute)."""
