@@ -320,6 +320,9 @@ DZ_CHAIN = _os.environ.get("FLUXDIST_DZ_CHAIN", "1") == "1"
 EPI_STATS = _os.environ.get("FLUXDIST_EPI_STATS", "1") != "0"  # BN statistics in the conv epilogues
 SIDE_WGRAD = _os.environ.get("FLUXDIST_SIDE_WGRAD", "1") != "0"  # wgrad kernels on a side stream (off the critical path)
 _SIDE = {}
+# CUDA stream priority of the weight-gradient side stream (0 = lowest; the step's capture stream uses FLUXDIST_MAIN_PRIO,
+# default -1: when both streams have CTAs pending, the critical path goes first)
+SIDE_PRIORITY = int(_os.environ.get("FLUXDIST_SIDE_PRIO", "0"))
 _SIDE_PENDING = set()
 
 
@@ -327,7 +330,7 @@ def _side_stream(device: torch.device) -> "torch.cuda.Stream":
     key = (device.index if device.index is not None else torch.cuda.current_device())
     s = _SIDE.get(key)
     if s is None:
-        s = _SIDE[key] = torch.cuda.Stream(device=device)
+        s = _SIDE[key] = torch.cuda.Stream(device=device, priority=SIDE_PRIORITY)
     return s
 
 

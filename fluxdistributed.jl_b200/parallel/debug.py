@@ -125,6 +125,8 @@ def verify_exchange(group, rounds: int = 2, raise_on_error: bool = True) -> Dict
                     r._launched = set()
                     if hasattr(comm, "set_step"):
                         comm.set_step(r, 0)
+                    if native:
+                        comm.status(r)  # read-and-clear: flags raised before this round (kept in the snapshot) are not ours
                     if native and k == 1:
                         aux = comm.plans[id(r)][1]
                         epochs0[id(r)] = aux["epoch"].clone()

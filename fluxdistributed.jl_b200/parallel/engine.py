@@ -13,6 +13,8 @@ N replicas in one process (task-based parallelism, one ``Trainer`` per device th
 """
 from __future__ import annotations
 
+import os
+
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -67,7 +69,7 @@ class GraphedStep:
             # high priority: the step's critical path (forward, BN backward, dgrad) is issued on this stream; the side
             # stream of the weight-gradient kernels keeps the default (lowest) priority, so when both have CTAs
             # pending the block scheduler places the critical-path ones first
-            s = torch.cuda.Stream(device=rep.dev.torch_device, priority=-1)
+            s = torch.cuda.Stream(device=rep.dev.torch_device, priority=int(os.environ.get("FLUXDIST_MAIN_PRIO", "-1")))
             s.wait_stream(torch.cuda.current_stream(rep.dev.torch_device))
             with torch.cuda.stream(s):
                 for _ in range(self.warmup):

@@ -269,6 +269,9 @@ class FusedReplica:
             comm = self.group.comm if self.group is not None else None
             if comm is not None and hasattr(comm, "plans") and id(self) in getattr(comm, "plans", {}):
                 snap["dev_step"] = comm.plans[id(self)][1]["step"].clone()
+                # the sticky status words too: a non-finite gradient seen during a graph warm-up on the (zero-filled)
+                # static buffers must not surface later as a training event
+                snap["dev_status"] = comm.plans[id(self)][1]["status"].clone()
         return snap
 
     def restore_state(self, snap: dict) -> None:
@@ -284,6 +287,8 @@ class FusedReplica:
             self.step_count = snap["step_count"]
             if "dev_step" in snap:
                 self.group.comm.plans[id(self)][1]["step"].copy_(snap["dev_step"])
+            if "dev_status" in snap:
+                self.group.comm.plans[id(self)][1]["status"].copy_(snap["dev_status"])
 
     def step(self, x, y, loss: Callable, fused_update: bool = True):
         if self.stream is not None:

@@ -912,6 +912,9 @@ def test_verify_exchange_single_gpu_native(opt):
     x = torch.randint(0, 256, (8, 32, 32, 3), dtype=torch.uint8, device="cuda")
     y = torch.randint(0, 10, (8,), device="cuda")
     tr.capture()
+    # the eager warm-up inside capture() runs on the zero-filled static buffers (degenerate BN statistics -> possibly
+    # non-finite gradients): whatever it raised in the sticky status words is restored with the rest of the state
+    assert tr.group.comm.status(tr.rep) == (False, False)
     tr.step(x, y)
     torch.cuda.synchronize()
     w1, s1 = tr.rep.arena.w32.clone(), [s.clone() for s in tr.rep.arena.slots]
