@@ -392,7 +392,10 @@ def bn_fwd_fused(y, gamma, beta, eps, ws, residual=None, relu=True, running_mean
 # the fused stem tail repeats the issue-bound arg-max gather in both BN-backward passes, and the halo dgrad of the
 # 64-channel stage is bound by its N=64 MMAs' shared-memory reads, which the longer epilogue competes with.
 POOL_BWD_FUSED = os.environ.get("FLUXDIST_POOL_BWD_FUSED", "0") == "1"
-HALO_DZ = os.environ.get("FLUXDIST_HALO_DZ", "0") == "1"  # dz epilogue in the halo dgrad (64-channel stage)
+# dz epilogue in the halo dgrad (64-channel stage).  Lost 0.1-1.4 % while every launch was stream-ordered; with the
+# tensor-core kernels chained by programmatic dependent launch it replaces six grid-barrier bn_bwd_fused launches (which
+# cannot be PDL dependents) by single-pass bn_bwd_apply: +1.8 % (21,838 -> 22,223 img/s, profiles/r2/policy_ab_pdl.txt)
+HALO_DZ = os.environ.get("FLUXDIST_HALO_DZ", "1") == "1"
 
 
 def bn_bwd_pool_fused(idx, g, y, mean, rstd, gamma, beta, ws, dgamma=None, dbeta=None):
