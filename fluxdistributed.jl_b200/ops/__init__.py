@@ -25,10 +25,38 @@ def _load():
         return _C
     try:
         _C = importlib.import_module("fluxdist._C")
+    except ModuleNotFoundError as e:
+        # the in-tree .so is missing (fresh checkout: it is git-ignored).  Build it once, under a file lock so that
+        # the ranks of a torchrun job do not compile concurrently; FLUXDIST_AUTOBUILD=0 turns this off.
+        _C, _C_ERR = _autobuild(e)
     except BaseException as e:  # noqa: BLE001 - recorded and re-raised by require_native
         _C_ERR = e
         _C = None
     return _C
+
+
+def _autobuild(first_error: BaseException):
+    if os.environ.get("FLUXDIST_AUTOBUILD", "1") == "0":
+        return None, first_error
+    try:
+        import fcntl
+        import importlib.util
+
+        here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location("fluxdist_build", os.path.join(here, "build.py"))
+        b = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(b)
+        with open(os.path.join(here, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            try:
+                if not os.path.exists(b.ext_path()):  # another rank may have built it while we waited
+                    b.build()
+            finally:
+                fcntl.flock(lk, fcntl.LOCK_UN)
+        importlib.invalidate_caches()
+        return importlib.import_module("fluxdist._C"), None
+    except BaseException as e:  # noqa: BLE001 - nvcc missing, compile error, ...: report both
+        return None, RuntimeError(f"{first_error!r}; automatic in-tree build failed: {e!r}")
 
 
 def native_available() -> bool:
