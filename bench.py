@@ -69,7 +69,8 @@ def reference_arm():
            "and no Julia toolchain exists in this image")
     if os.path.isdir(ref_dir) and os.listdir(ref_dir):
         why = "baseline/_ref present but the reference is Julia code; no Julia runtime in this image"
-    print(json.dumps({"impl": "reference", "unavailable": why}))
+    if int(os.environ.get("RANK", "0")) == 0:  # under torchrun every rank gets here: one line, from rank 0
+        print(json.dumps({"impl": "reference", "unavailable": why}))
 
 
 METRIC = {"resnet34": "ResNet-34 ImageNet-shape training throughput"}
