@@ -115,6 +115,30 @@ def build(verbose: bool = False, force: bool = False) -> str:
     return out
 
 
+def build_staging_mock(tsan: bool = False, force: bool = False) -> str:
+    """Host-only build of the pinned staging ring over the mock CUDA runtime (``csrc/mock``): module ``_Cstaging_mock``
+    for ``tests/test_staging_mock.py``.  g++ only — no nvcc, no torch.  ``tsan=True`` instruments it with
+    ThreadSanitizer (``_Cstaging_mock_tsan``; run the test with ``LD_PRELOAD=$(gcc -print-file-name=libtsan.so)``,
+    see scripts/sanitize.sh)."""
+    import pybind11
+
+    name = "_Cstaging_mock_tsan" if tsan else "_Cstaging_mock"
+    out = ext_path(name)
+    srcs = [os.path.join(CSRC, "staging.cpp"), os.path.join(CSRC, "mock", "staging_mock_bind.cpp")]
+    deps = srcs + [os.path.join(CSRC, "mock", "staging_mock_cuda.h"), os.path.join(CSRC, "staging.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-DFD_STAGING_MOCK_CUDA",
+           f"-I{pybind11.get_include()}", f"-I{sysconfig.get_paths()['include']}", f"-I{CSRC}"]
+    if tsan:
+        cmd += ["-fsanitize=thread", "-DFD_MOCK_MODNAME=_Cstaging_mock_tsan"]
+    cmd += srcs + ["-o", out]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("staging mock build failed:\n" + r.stderr[-4000:])
+    return out
+
+
 def ptxas_report() -> str:
     """Concatenate the per-file ``-Xptxas -v`` logs (registers / spills / smem)."""
     out = []

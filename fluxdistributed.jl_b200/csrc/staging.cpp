@@ -15,7 +15,11 @@
 // the next next() call.  The H2D copy of step i+1 (and i+2) therefore overlaps step i's compute whichever side is
 // ahead.  All queue state (free / ready / in flight) is guarded by one mutex; the CUDA calls made under it are
 // asynchronous enqueues.
+#ifdef FD_STAGING_MOCK_CUDA
+#include "mock/staging_mock_cuda.h"  // host-only protocol tests (tests/test_staging_mock.py); never defined for the product
+#else
 #include <cuda_runtime.h>
+#endif
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
