@@ -543,6 +543,15 @@ def main():
             "e2e": e2e, "gpu_launches": launches, "final_loss": final_loss,
             "nonfinite_grad": bool(nanflag), "barrier_timeout": bool(timeout), "replicas_synced": synced,
         }
+        if args.impl == "native":
+            try:  # launch policy of the native path, for the record (never allowed to break the line)
+                from fluxdist import ops as _ops
+                from fluxdist.ops import native as _nat
+
+                rec["config"]["launch"] = {"pdl_mask": int(_ops.extension().pdl_mask()), "halo_dz": bool(_nat.HALO_DZ),
+                                           "side_stream_wgrad": bool(_nat.SIDE_WGRAD)}
+            except Exception:  # noqa: BLE001
+                pass
         print(json.dumps(rec), flush=True)
     if world > 1:
         if args.impl == "ddp_tuned":
